@@ -1,0 +1,745 @@
+// libmcq: C ABI + host orchestration for the B200 annealing engine (see include/mcq.h).
+//
+// Host side of the hot path: what run_experiment (experiments.py:475-573) does with a process
+// pool -- start n_runs chains, collect histories / best energies / accept lists -- is done here
+// as a handful of kernel launches over a batch of chains resident in shared memory.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/mcq.h"
+#include "anneal.cuh"
+
+namespace mcq {
+
+static thread_local std::string g_err;
+
+static int fail(int code, const std::string &msg) {
+    g_err = msg;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess) {                                                                    \
+            char _b[512];                                                                           \
+            snprintf(_b, sizeof _b, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return fail(MCQ_ECUDA, _b);                                                             \
+        }                                                                                           \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------
+// geometry shared by host and device
+// ------------------------------------------------------------------------------------------
+static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+// idx = x*i + y*j + z*k + w for the 13 line families (oracle/queens_numpy.py: line_ids).
+// Board mode has no (i,j) family; its counters start at family 1.
+static int make_coefs(int full, int N, int4 coef[NFAM]) {
+    const int W = 2 * N - 1, o = N - 1;
+    const int sz_axis = N * N, sz_plane = N * W, sz_space = W * W;
+    int base[NFAM];
+    int b = 0;
+    for (int f = 0; f < NFAM; ++f) {
+        if (f == 0 && !full) { base[f] = 0; continue; }
+        base[f] = b;
+        b += f < 3 ? sz_axis : f < 9 ? sz_plane : sz_space;
+    }
+    coef[0] = make_int4(N, 1, 0, base[0]);
+    coef[1] = make_int4(N, 0, 1, base[1]);
+    coef[2] = make_int4(0, N, 1, base[2]);
+    coef[3] = make_int4(1, -1, W, base[3] + o);
+    coef[4] = make_int4(1, 1, W, base[4]);
+    coef[5] = make_int4(1, W, -1, base[5] + o);
+    coef[6] = make_int4(1, W, 1, base[6]);
+    coef[7] = make_int4(W, 1, -1, base[7] + o);
+    coef[8] = make_int4(W, 1, 1, base[8]);
+    coef[9] = make_int4(W + 1, -W, -1, base[9] + o * W + o);
+    coef[10] = make_int4(W + 1, -W, 1, base[10] + o * W);
+    coef[11] = make_int4(W + 1, W, -1, base[11] + o);
+    coef[12] = make_int4(W + 1, W, 1, base[12]);
+    return b;  // total counter bytes
+}
+
+static Layout make_layout(int full, int N, int Q, int G) {
+    Layout L;
+    int4 tmp[NFAM];
+    L.n_cnt = round_up(make_coefs(full, N, tmp), 4);
+    L.pos32 = (full && N > 32) ? 1 : 0;
+    L.off_state = L.n_cnt;
+    int state_b = full ? Q * (L.pos32 ? 4 : 2) : N * N;
+    L.off_occ = round_up(L.off_state + state_b, 4);
+    int occ_b = full ? round_up((N * N * N + 31) / 32 * 4, 4) : 0;
+    L.off_pkt = round_up(L.off_occ + occ_b, 16);
+    L.pb = G < 8 ? G : 8;
+    L.off_hst = L.off_pkt + L.pb * PKT_BYTES;
+    L.stride = round_up(L.off_hst + HBLK * 4, 16);
+    return L;
+}
+
+static inline int state_bytes_of(int mode, int n, int q) { return mode == MCQ_MODE_FULL3D ? 3 * q : n * n; }
+
+// ------------------------------------------------------------------------------------------
+// small kernels: initial states, energies, delta probes, cross-replica statistics
+// ------------------------------------------------------------------------------------------
+__host__ __device__ static inline int gcd_int(int a, int b) {
+    while (b) { int t = a % b; a = b; b = t; }
+    return a;
+}
+
+// One thread per chain.  Distribution-identical to mcmc_board.py:26-59 / mcmc.py:20-101 (the
+// reference consumes MT19937; we consume Philox in the INIT domain of the chain's key).
+__global__ void init_states_kernel(int full, int N, int Q, int init_mode, int n_chains,
+                                   const unsigned long long *seeds, uint8_t *state, int state_bytes,
+                                   uint32_t *occ_scratch, int occ_words) {
+    const int chain = blockIdx.x * blockDim.x + threadIdx.x;
+    if (chain >= n_chains) return;
+    const unsigned long long sd = seeds ? seeds[chain] : 0ull;
+    const uint32_t k0 = (uint32_t)sd, k1 = (uint32_t)(sd >> 32);
+    uint8_t *st = state + (size_t)chain * state_bytes;
+    uint32_t ctr = 0;
+    Philox4 r;
+    int have = 0;
+    auto next_word = [&]() -> uint32_t {
+        if (have == 0) { r = philox4x32_10(ctr++, 0u, 0u, PHILOX_DOMAIN_INIT, k0, k1); have = 4; }
+        const uint32_t v = have == 4 ? r.x : have == 3 ? r.y : have == 2 ? r.z : r.w;
+        --have;
+        return v;
+    };
+    int M = N;  // Klarner core edge
+    if (init_mode == MCQ_INIT_KLARNER && gcd_int(N, 210) != 1) {
+        for (M = N - 1; M > 0; --M) if (gcd_int(M, 210) == 1) break;
+    }
+    if (!full) {
+        for (int i = 0; i < N; ++i)
+            for (int j = 0; j < N; ++j) {
+                int k;
+                if (init_mode == MCQ_INIT_LATIN) k = (i + j) % N;
+                else if (init_mode == MCQ_INIT_KLARNER && i < M && j < M) k = (3 * i + 5 * j) % M;
+                else k = (int)__umulhi(next_word(), (uint32_t)N);
+                st[i * N + j] = (uint8_t)k;
+            }
+        return;
+    }
+    uint32_t *occ = occ_scratch + (size_t)chain * occ_words;
+    for (int w = 0; w < occ_words; ++w) occ[w] = 0u;
+    int placed = 0;
+    if (init_mode == MCQ_INIT_LATIN || init_mode == MCQ_INIT_KLARNER) {
+        const int edge = init_mode == MCQ_INIT_LATIN ? N : M;
+        for (int i = 0; i < edge; ++i)
+            for (int j = 0; j < edge; ++j) {
+                const int k = init_mode == MCQ_INIT_LATIN ? (i + j) % N : (3 * i + 5 * j) % M;
+                st[3 * placed] = (uint8_t)i; st[3 * placed + 1] = (uint8_t)j; st[3 * placed + 2] = (uint8_t)k;
+                const int cid = (i * N + j) * N + k;
+                occ[cid >> 5] |= 1u << (cid & 31);
+                ++placed;
+            }
+    }
+    while (placed < Q) {  // uniformly random unused cells, in order (== choice(replace=False))
+        uint32_t w = next_word();
+        const int i = draw_digit(w, N), j = draw_digit(w, N), k = draw_digit(w, N);
+        const int cid = (i * N + j) * N + k;
+        if ((occ[cid >> 5] >> (cid & 31)) & 1u) continue;
+        occ[cid >> 5] |= 1u << (cid & 31);
+        st[3 * placed] = (uint8_t)i; st[3 * placed + 1] = (uint8_t)j; st[3 * placed + 2] = (uint8_t)k;
+        ++placed;
+    }
+}
+
+// one warp per state: E = sum over attack lines of C(count,2)
+__global__ void __launch_bounds__(32) energy_kernel(const __grid_constant__ KArgs a, int *out) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int b = blockIdx.x;
+    const int e = build_chain<32>(a, smem, a.state + (size_t)b * a.state_bytes, true, threadIdx.x);
+    if (threadIdx.x == 0) out[b] = e;
+}
+
+// one warp per state: delta-E of each candidate move with the same LineEval the chain uses
+__global__ void __launch_bounds__(32) delta_kernel(const __grid_constant__ KArgs a, int n_moves, const uint32_t *moves,
+                                                    int *out) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int b = blockIdx.x, g = threadIdx.x;
+    build_chain<32>(a, smem, a.state + (size_t)b * a.state_bytes, true, g);
+    LaneLines<32> L;
+    L.init(a, g);
+    const unsigned char *st = smem + a.lay.off_state;
+    for (int m = 0; m < n_moves; ++m) {
+        const uint32_t w = moves[(size_t)b * n_moves + m];
+        int i0, j0, k0, i1, j1, k1;
+        if (a.full) {
+            const int q = w & 0xfff;
+            i1 = (w >> 12) & 63; j1 = (w >> 18) & 63; k1 = (w >> 24) & 63;
+            unpack_pos(a.lay.pos32, load_pos(st, a.lay.pos32, q), i0, j0, k0);
+        } else {
+            i0 = i1 = w & 255; j0 = j1 = (w >> 8) & 255; k1 = (w >> 16) & 255;
+            k0 = st[i0 * a.N + j0];
+        }
+        LineEval<32> ev;
+        const int d = group_sum<32>(ev.eval(L, smem, i0, j0, k0, i1, j1, k1));
+        if (g == 0) out[(size_t)b * n_moves + m] = d;
+    }
+}
+
+// Column sums of a [chain][step] history tile: per group, sum E and sum E^2 (experiments.py:593-595).
+// grid.x tiles the columns, grid.y slices the chains; partial sums go out with 64-bit atomics.
+template <typename T>
+__global__ void stats_kernel(const T *hist, long long pitch, int n_cols, long long h_origin, int n_chains,
+                             const int *group, const int *steps_done, unsigned long long *sum_e,
+                             unsigned long long *sum_e2, long long stat_pitch) {
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= n_cols) return;
+    const long long h = h_origin + col;
+    const int per = (n_chains + gridDim.y - 1) / gridDim.y;
+    const int c0 = blockIdx.y * per, c1 = min(n_chains, c0 + per);
+    unsigned long long s = 0, s2 = 0;
+    int cur = -1;
+    for (int c = c0; c < c1; ++c) {
+        const int gr = group ? group[c] : 0;
+        if (gr != cur) {
+            if (cur >= 0 && (s | s2)) {
+                atomicAdd(&sum_e[(size_t)cur * stat_pitch + h], s);
+                atomicAdd(&sum_e2[(size_t)cur * stat_pitch + h], s2);
+            }
+            cur = gr; s = 0; s2 = 0;
+        }
+        if (h > steps_done[c]) continue;  // early-stopped chain: no energy appended here
+        const unsigned long long v = (unsigned long long)hist[(size_t)c * pitch + col];
+        s += v; s2 += v * v;
+    }
+    if (cur >= 0 && (s | s2)) {
+        atomicAdd(&sum_e[(size_t)cur * stat_pitch + h], s);
+        atomicAdd(&sum_e2[(size_t)cur * stat_pitch + h], s2);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// context: device, streams, grow-only scratch
+// ------------------------------------------------------------------------------------------
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return 0;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        if (cudaMalloc(&p, want) != cudaSuccess) { cudaGetLastError(); return -1; }
+        cap = want;
+        return 0;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+enum BufId {
+    B_SEEDS, B_GROUP, B_BETA, B_INIT, B_RMOVES, B_RUNIF, B_STATE, B_BEST, B_REC, B_OCC, B_HIST0, B_HIST1,
+    B_ABITS, B_ACCH, B_BINS, B_STATE_IN, B_MOVES, B_OUT, B_SUME, B_SUME2, B_NBUF
+};
+
+}  // namespace mcq
+
+struct mcq_ctx {
+    int device;
+    cudaStream_t stream;
+    cudaStream_t copy_stream;
+    cudaDeviceProp prop;
+    mcq::DevBuf buf[mcq::B_NBUF];
+};
+
+namespace mcq {
+
+template <int G, bool FULL, bool REPLAY>
+static cudaError_t launch_one(const KArgs &a, int grid, int block, size_t smem, cudaStream_t s) {
+    auto k = anneal_kernel<G, FULL, REPLAY>;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    k<<<grid, block, smem, s>>>(a);
+    return cudaGetLastError();
+}
+
+template <int G>
+static cudaError_t launch_g(const KArgs &a, bool replay, int grid, int block, size_t smem, cudaStream_t s) {
+    if (a.full) return replay ? launch_one<G, true, true>(a, grid, block, smem, s) : launch_one<G, true, false>(a, grid, block, smem, s);
+    return replay ? launch_one<G, false, true>(a, grid, block, smem, s) : launch_one<G, false, false>(a, grid, block, smem, s);
+}
+
+static cudaError_t launch_anneal(int G, const KArgs &a, bool replay, int grid, int block, size_t smem, cudaStream_t s) {
+    switch (G) {
+        case 4: return launch_g<4>(a, replay, grid, block, smem, s);
+        case 8: return launch_g<8>(a, replay, grid, block, smem, s);
+        case 16: return launch_g<16>(a, replay, grid, block, smem, s);
+        default: return launch_g<32>(a, replay, grid, block, smem, s);
+    }
+}
+
+static int check_problem(int mode, int n, int q) {
+    if (mode != MCQ_MODE_BOARD && mode != MCQ_MODE_FULL3D) return fail(MCQ_EINVAL, "mode must be MCQ_MODE_BOARD or MCQ_MODE_FULL3D");
+    if (n < 2 || n > 64) return fail(MCQ_EINVAL, "N must be in [2, 64]");
+    if (mode == MCQ_MODE_BOARD && q != n * n) return fail(MCQ_EINVAL, "board mode requires Q == N*N");
+    if (q < 1 || q > 4096) return fail(MCQ_EINVAL, "Q must be in [1, 4096]");
+    if (mode == MCQ_MODE_FULL3D && (long long)q >= (long long)n * n * n) return fail(MCQ_EINVAL, "full_3d requires Q < N^3 (an empty cell to move to)");
+    return 0;
+}
+
+// copy `bytes` from a caller buffer (host or device) into scratch `b`; returns device pointer
+static int stage_in(mcq_ctx *ctx, int b, const void *src, size_t bytes, int mem, cudaStream_t s, void **out) {
+    if (mem == MCQ_MEM_DEVICE) { *out = const_cast<void *>(src); return 0; }
+    if (ctx->buf[b].ensure(bytes)) return fail(MCQ_ENOMEM, "device allocation failed");
+    CUDA_TRY(cudaMemcpyAsync(ctx->buf[b].p, src, bytes, cudaMemcpyHostToDevice, s));
+    *out = ctx->buf[b].p;
+    return 0;
+}
+
+static int copy_out(void *dst, const void *src_dev, size_t bytes, int mem, cudaStream_t s) {
+    if (!dst) return 0;
+    CUDA_TRY(cudaMemcpyAsync(dst, src_dev, bytes, mem == MCQ_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
+    return 0;
+}
+
+}  // namespace mcq
+
+using namespace mcq;
+
+extern "C" {
+
+int mcq_abi_version(void) { return MCQ_ABI_VERSION; }
+
+int mcq_sizeof_run_params(void) { return (int)sizeof(mcq_run_params); }
+
+const char *mcq_last_error(void) { return g_err.c_str(); }
+
+int mcq_device_count(int *count) {
+    if (!count) return fail(MCQ_EINVAL, "count is NULL");
+    cudaError_t e = cudaGetDeviceCount(count);
+    if (e != cudaSuccess) { *count = 0; cudaGetLastError(); return fail(MCQ_ECUDA, cudaGetErrorString(e)); }
+    return 0;
+}
+
+int mcq_create(int device, mcq_ctx **out) {
+    if (!out) return fail(MCQ_EINVAL, "out is NULL");
+    *out = nullptr;
+    int n = 0;
+    CUDA_TRY(cudaGetDeviceCount(&n));
+    if (device < 0 || device >= n) return fail(MCQ_EINVAL, "no such CUDA device");
+    CUDA_TRY(cudaSetDevice(device));
+    mcq_ctx *c = new mcq_ctx();
+    c->device = device;
+    CUDA_TRY(cudaGetDeviceProperties(&c->prop, device));
+    if (c->prop.major < 10) {
+        delete c;
+        return fail(MCQ_ECUDA, "libmcq is built for sm_100a (B200) only; this device is older");
+    }
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    *out = c;
+    return 0;
+}
+
+int mcq_destroy(mcq_ctx *ctx) {
+    if (!ctx) return 0;
+    cudaSetDevice(ctx->device);
+    for (auto &b : ctx->buf) b.release();
+    cudaStreamDestroy(ctx->stream);
+    cudaStreamDestroy(ctx->copy_stream);
+    delete ctx;
+    return 0;
+}
+
+int mcq_device_info(mcq_ctx *ctx, int *sm_count, int *smem_per_sm, int *smem_per_block_optin, int *clock_khz,
+                    char *name, int name_len) {
+    if (!ctx) return fail(MCQ_EINVAL, "ctx is NULL");
+    if (sm_count) *sm_count = ctx->prop.multiProcessorCount;
+    if (smem_per_sm) *smem_per_sm = (int)ctx->prop.sharedMemPerMultiprocessor;
+    if (smem_per_block_optin) *smem_per_block_optin = (int)ctx->prop.sharedMemPerBlockOptin;
+    if (clock_khz) *clock_khz = ctx->prop.clockRate;
+    if (name && name_len > 0) { strncpy(name, ctx->prop.name, name_len - 1); name[name_len - 1] = 0; }
+    return 0;
+}
+
+int mcq_state_bytes(int mode, int n, int q) {
+    if (check_problem(mode, n, q)) return MCQ_EINVAL;
+    return state_bytes_of(mode, n, q);
+}
+
+int mcq_chain_smem_bytes(int mode, int n, int q, int lanes_per_chain) {
+    if (check_problem(mode, n, q)) return MCQ_EINVAL;
+    if (lanes_per_chain != 4 && lanes_per_chain != 8 && lanes_per_chain != 16 && lanes_per_chain != 32)
+        return fail(MCQ_EINVAL, "lanes_per_chain must be 4, 8, 16 or 32");
+    return make_layout(mode == MCQ_MODE_FULL3D, n, q, lanes_per_chain).stride;
+}
+
+int mcq_host_alloc(void **ptr, uint64_t bytes) {
+    if (!ptr) return fail(MCQ_EINVAL, "ptr is NULL");
+    CUDA_TRY(cudaHostAlloc(ptr, (size_t)bytes, cudaHostAllocDefault));
+    return 0;
+}
+
+int mcq_host_free(void *ptr) {
+    if (ptr) CUDA_TRY(cudaFreeHost(ptr));
+    return 0;
+}
+
+void mcq_philox4x32_10(const uint32_t counter[4], const uint32_t key[2], uint32_t out[4]) {
+    const Philox4 r = philox4x32_10(counter[0], counter[1], counter[2], counter[3], key[0], key[1]);
+    out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
+}
+
+static int probe_common(mcq_ctx *ctx, int mode, int n, int q, int n_states, const uint8_t *states, int mem,
+                        cudaStream_t s, KArgs &a) {
+    if (!ctx) return fail(MCQ_EINVAL, "ctx is NULL");
+    if (int rc = check_problem(mode, n, q)) return rc;
+    if (n_states < 0 || (!states && n_states)) return fail(MCQ_EINVAL, "states is NULL");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    memset(&a, 0, sizeof a);
+    a.full = mode == MCQ_MODE_FULL3D;
+    a.N = n; a.Q = q; a.n_chains = n_states;
+    a.lay = make_layout(a.full, n, q, 32);
+    make_coefs(a.full, n, a.coef);
+    a.state_bytes = state_bytes_of(mode, n, q);
+    if ((size_t)a.lay.stride > ctx->prop.sharedMemPerBlockOptin) return fail(MCQ_ENOMEM, "one chain does not fit in shared memory");
+    void *d = nullptr;
+    if (int rc = stage_in(ctx, B_STATE_IN, states, (size_t)n_states * a.state_bytes, mem, s, &d)) return rc;
+    a.state = static_cast<uint8_t *>(d);
+    return 0;
+}
+
+int mcq_energy(mcq_ctx *ctx, int mode, int n, int q, int n_states, const uint8_t *states, int32_t *out_energy,
+               int mem, void *stream) {
+    if (!out_energy && n_states) return fail(MCQ_EINVAL, "out_energy is NULL");
+    cudaStream_t s = stream ? (cudaStream_t)stream : (ctx ? ctx->stream : nullptr);
+    KArgs a;
+    if (int rc = probe_common(ctx, mode, n, q, n_states, states, mem, s, a)) return rc;
+    if (n_states == 0) return 0;
+    int *d_out = out_energy;
+    if (mem == MCQ_MEM_HOST) {
+        if (ctx->buf[B_OUT].ensure((size_t)n_states * 4)) return fail(MCQ_ENOMEM, "device allocation failed");
+        d_out = static_cast<int *>(ctx->buf[B_OUT].p);
+    }
+    CUDA_TRY(cudaFuncSetAttribute(energy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, a.lay.stride));
+    energy_kernel<<<n_states, 32, a.lay.stride, s>>>(a, d_out);
+    CUDA_TRY(cudaGetLastError());
+    if (mem == MCQ_MEM_HOST) CUDA_TRY(cudaMemcpyAsync(out_energy, d_out, (size_t)n_states * 4, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return 0;
+}
+
+int mcq_delta_energy(mcq_ctx *ctx, int mode, int n, int q, int n_states, const uint8_t *states, int n_moves,
+                     const uint32_t *moves, int32_t *out_delta, int mem, void *stream) {
+    if ((!out_delta || !moves) && n_states && n_moves) return fail(MCQ_EINVAL, "moves/out_delta is NULL");
+    cudaStream_t s = stream ? (cudaStream_t)stream : (ctx ? ctx->stream : nullptr);
+    KArgs a;
+    if (int rc = probe_common(ctx, mode, n, q, n_states, states, mem, s, a)) return rc;
+    if (n_states == 0 || n_moves <= 0) return 0;
+    const size_t cnt = (size_t)n_states * n_moves;
+    void *d_moves = nullptr;
+    if (int rc = stage_in(ctx, B_MOVES, moves, cnt * 4, mem, s, &d_moves)) return rc;
+    int *d_out = out_delta;
+    if (mem == MCQ_MEM_HOST) {
+        if (ctx->buf[B_OUT].ensure(cnt * 4)) return fail(MCQ_ENOMEM, "device allocation failed");
+        d_out = static_cast<int *>(ctx->buf[B_OUT].p);
+    }
+    CUDA_TRY(cudaFuncSetAttribute(delta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, a.lay.stride));
+    delta_kernel<<<n_states, 32, a.lay.stride, s>>>(a, n_moves, static_cast<const uint32_t *>(d_moves), d_out);
+    CUDA_TRY(cudaGetLastError());
+    if (mem == MCQ_MEM_HOST) CUDA_TRY(cudaMemcpyAsync(out_delta, d_out, cnt * 4, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return 0;
+}
+
+int mcq_run(mcq_ctx *ctx, const mcq_run_params *p) {
+    if (!ctx || !p) return fail(MCQ_EINVAL, "ctx/params is NULL");
+    if (p->struct_size != sizeof(mcq_run_params)) return fail(MCQ_EINVAL, "mcq_run_params size mismatch (ABI)");
+    if (int rc = check_problem(p->mode, p->n, p->q)) return rc;
+    if (p->n_steps < 0) return fail(MCQ_EINVAL, "n_steps must be >= 0");
+    if (p->n_chains < 0) return fail(MCQ_EINVAL, "n_chains must be >= 0");
+    if (p->n_groups < 1) return fail(MCQ_EINVAL, "n_groups must be >= 1");
+    if (p->init_mode < MCQ_INIT_RANDOM || p->init_mode > MCQ_INIT_EXPLICIT) return fail(MCQ_EINVAL, "unknown init_mode");
+    if (p->init_mode == MCQ_INIT_EXPLICIT && !p->init_states && p->n_chains) return fail(MCQ_EINVAL, "init_states required for MCQ_INIT_EXPLICIT");
+    if ((p->init_mode == MCQ_INIT_LATIN || p->init_mode == MCQ_INIT_KLARNER) && p->q != p->n * p->n)
+        return fail(MCQ_EINVAL, "latin/klarner initialization assumes Q = N^2");
+    const bool replay = p->replay_moves != nullptr;
+    if (replay && (!p->replay_uniforms || !p->beta_f64)) return fail(MCQ_EINVAL, "replay needs replay_moves, replay_uniforms and beta_f64");
+    if (!replay && !p->beta_log2e && p->n_steps > 0) return fail(MCQ_EINVAL, "beta_log2e is NULL");
+    if (p->mem != MCQ_MEM_HOST && p->mem != MCQ_MEM_DEVICE) return fail(MCQ_EINVAL, "mem must be MCQ_MEM_HOST or MCQ_MEM_DEVICE");
+    const bool want_hist = p->hist_dtype != MCQ_HIST_NONE && p->energy_history;
+    const bool want_stats = p->stat_sum_e || p->stat_sum_e2;
+    if (want_stats && !(p->stat_sum_e && p->stat_sum_e2)) return fail(MCQ_EINVAL, "stat_sum_e and stat_sum_e2 go together");
+    if (p->hist_dtype < MCQ_HIST_NONE || p->hist_dtype > MCQ_HIST_I32) return fail(MCQ_EINVAL, "unknown hist_dtype");
+    if (want_hist && p->hist_pitch < (int64_t)p->n_steps + 1) return fail(MCQ_EINVAL, "hist_pitch must be >= n_steps+1");
+    const long long e_max = 13LL * p->q * (p->n - 1) / 2;
+    if (want_hist && p->hist_dtype == MCQ_HIST_U16 && e_max >= 65536) return fail(MCQ_EINVAL, "uint16 history would overflow for this N; use MCQ_HIST_I32");
+    if (p->n_bins < 0 || (p->n_bins > 0 && (!p->bin_starts || !p->accept_hist))) return fail(MCQ_EINVAL, "n_bins > 0 needs bin_starts and accept_hist");
+    if (p->n_chains == 0) { if (p->kernel_ms) *p->kernel_ms = 0.f; if (p->gpu_launches) *p->gpu_launches = 0; return 0; }
+
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t s = p->stream ? (cudaStream_t)p->stream : ctx->stream;
+    const int mem = p->mem;
+    const int full = p->mode == MCQ_MODE_FULL3D;
+    const int nc = p->n_chains, ns = p->n_steps;
+    const int sbytes = state_bytes_of(p->mode, p->n, p->q);
+    int launches = 0;
+
+    // ---- geometry ----
+    const size_t smem_block = ctx->prop.sharedMemPerBlockOptin;
+    const size_t smem_sm = ctx->prop.sharedMemPerMultiprocessor;
+    int G = p->lanes_per_chain;
+    if (G != 0 && G != 4 && G != 8 && G != 16 && G != 32) return fail(MCQ_EINVAL, "lanes_per_chain must be 0, 4, 8, 16 or 32");
+    if (G == 0) {
+        G = 8;
+        while (G < 32 && (size_t)make_layout(full, p->n, p->q, G).stride * (32 / G) > smem_block) G *= 2;
+    }
+    Layout lay = make_layout(full, p->n, p->q, G);
+    if ((size_t)lay.stride * (32 / G) > smem_block) return fail(MCQ_ENOMEM, "a warp's chains do not fit in shared memory; raise lanes_per_chain");
+    int wpc = p->warps_per_cta;
+    if (wpc < 0 || wpc > 8) return fail(MCQ_EINVAL, "warps_per_cta must be in [0, 8]");
+    int best_w = 1, best_chains = 0, best_ctas = 1;
+    for (int w = 8; w >= 1; --w) {
+        if (wpc && w != wpc) continue;
+        const int cpc_w = w * 32 / G;
+        const size_t need = (size_t)cpc_w * lay.stride;
+        if (need > smem_block) continue;
+        int ctas = (int)std::min<size_t>(32, smem_sm / (need + 1024));
+        ctas = std::min(ctas, 64 / w);
+        if (ctas * cpc_w > best_chains) { best_chains = ctas * cpc_w; best_w = w; best_ctas = ctas; }
+    }
+    if (best_chains == 0) return fail(MCQ_ENOMEM, "requested warps_per_cta does not fit in shared memory");
+    const int cpc = best_w * 32 / G;
+    const int block = best_w * 32;
+    const int grid = (nc + cpc - 1) / cpc;
+    size_t smem = (size_t)cpc * lay.stride;
+    {   // cap residency (explicit limit, or balance the waves) by padding the shared-memory request
+        int ctas = best_ctas;
+        const int sms = ctx->prop.multiProcessorCount;
+        if (p->max_chains_per_sm > 0) ctas = std::max(1, std::min(ctas, p->max_chains_per_sm / cpc));
+        else {
+            const long long resident = (long long)sms * ctas;
+            const long long waves = (grid + resident - 1) / resident;
+            const int per_sm = (int)((grid + sms * waves - 1) / (sms * waves));
+            ctas = std::max(1, std::min(ctas, per_sm));
+        }
+        if (ctas < best_ctas) {
+            size_t pad = smem_sm / ctas - 1024;
+            pad = std::min(pad, smem_block) & ~(size_t)15;
+            smem = std::max(smem, pad);
+        }
+    }
+
+    // ---- inputs ----
+    KArgs a;
+    memset(&a, 0, sizeof a);
+    a.full = full; a.N = p->n; a.Q = p->q; a.n_chains = nc; a.n_steps = ns;
+    a.patience = (!full && p->early_stop_patience >= 0) ? p->early_stop_patience : -1;
+    a.lay = lay;
+    make_coefs(full, p->n, a.coef);
+    a.state_bytes = sbytes;
+    void *d = nullptr;
+    if (p->chain_seeds) { if (int rc = stage_in(ctx, B_SEEDS, p->chain_seeds, (size_t)nc * 8, mem, s, &d)) return rc; a.seeds = static_cast<unsigned long long *>(d); }
+    if (p->chain_group) { if (int rc = stage_in(ctx, B_GROUP, p->chain_group, (size_t)nc * 4, mem, s, &d)) return rc; a.group = static_cast<int *>(d); }
+    if (replay) {
+        if (int rc = stage_in(ctx, B_BETA, p->beta_f64, (size_t)p->n_groups * ns * 8, mem, s, &d)) return rc; a.beta64 = static_cast<double *>(d);
+        if (int rc = stage_in(ctx, B_RMOVES, p->replay_moves, (size_t)nc * ns * 4, mem, s, &d)) return rc; a.rmoves = static_cast<uint32_t *>(d);
+        if (int rc = stage_in(ctx, B_RUNIF, p->replay_uniforms, (size_t)nc * ns * 8, mem, s, &d)) return rc; a.runif = static_cast<double *>(d);
+    } else if (ns > 0) {
+        if (int rc = stage_in(ctx, B_BETA, p->beta_log2e, (size_t)p->n_groups * ns * 4, mem, s, &d)) return rc; a.beta_c = static_cast<float *>(d);
+    }
+
+    // ---- persistent record (always internal scratch; copied to the caller's arrays at the end) ----
+    // layout of B_REC: 9 int arrays of nc + 1 word for replay_err
+    if (ctx->buf[B_REC].ensure(((size_t)nc * 9 + 4) * 4)) return fail(MCQ_ENOMEM, "device allocation failed");
+    int *rec = static_cast<int *>(ctx->buf[B_REC].p);
+    a.init_e = rec; a.cur_e = rec + nc; a.best_e = rec + 2 * (size_t)nc; a.best_step = rec + 3 * (size_t)nc;
+    a.n_acc = rec + 4 * (size_t)nc; a.steps_done = rec + 5 * (size_t)nc; a.stale = rec + 6 * (size_t)nc;
+    a.bin_mark = rec + 7 * (size_t)nc; a.near_cnt = reinterpret_cast<uint32_t *>(rec + 8 * (size_t)nc);
+    a.replay_err = reinterpret_cast<uint32_t *>(rec + 9 * (size_t)nc);
+    CUDA_TRY(cudaMemsetAsync(rec, 0, ((size_t)nc * 9 + 4) * 4, s));
+    if (ctx->buf[B_STATE].ensure((size_t)nc * sbytes) || ctx->buf[B_BEST].ensure((size_t)nc * sbytes)) return fail(MCQ_ENOMEM, "device allocation failed");
+    a.state = static_cast<uint8_t *>(ctx->buf[B_STATE].p);
+    a.best_state = static_cast<uint8_t *>(ctx->buf[B_BEST].p);
+
+    // ---- initial states ----
+    if (p->init_mode == MCQ_INIT_EXPLICIT) {
+        CUDA_TRY(cudaMemcpyAsync(a.state, p->init_states, (size_t)nc * sbytes,
+                                 mem == MCQ_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
+    } else {
+        const int occ_words = full ? (p->n * p->n * p->n + 31) / 32 : 0;
+        if (full && ctx->buf[B_OCC].ensure((size_t)nc * occ_words * 4)) return fail(MCQ_ENOMEM, "device allocation failed");
+        init_states_kernel<<<(nc + 127) / 128, 128, 0, s>>>(full, p->n, p->q, p->init_mode, nc, a.seeds, a.state, sbytes,
+                                                             static_cast<uint32_t *>(ctx->buf[B_OCC].p), occ_words);
+        CUDA_TRY(cudaGetLastError());
+        ++launches;
+    }
+    CUDA_TRY(cudaMemcpyAsync(a.best_state, a.state, (size_t)nc * sbytes, cudaMemcpyDeviceToDevice, s));
+
+    // ---- acceptance bins ----
+    a.n_bins = p->n_bins;
+    if (p->n_bins > 0) {
+        if (p->bin_starts[0] != 0 || p->bin_starts[p->n_bins] != ns) return fail(MCQ_EINVAL, "bin_starts must run from 0 to n_steps");
+        for (int b = 0; b < p->n_bins; ++b) if (p->bin_starts[b] > p->bin_starts[b + 1]) return fail(MCQ_EINVAL, "bin_starts must be non-decreasing");
+        if (ctx->buf[B_BINS].ensure((size_t)(p->n_bins + 2) * 4)) return fail(MCQ_ENOMEM, "device allocation failed");
+        std::vector<int> bs(p->bin_starts, p->bin_starts + p->n_bins + 1);
+        bs.push_back(0x7fffffff);
+        CUDA_TRY(cudaMemcpyAsync(ctx->buf[B_BINS].p, bs.data(), bs.size() * 4, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(cudaStreamSynchronize(s));  // bs is a stack temporary
+        a.bin_starts = static_cast<int *>(ctx->buf[B_BINS].p);
+        if (mem == MCQ_MEM_DEVICE) a.acc_hist = p->accept_hist;
+        else {
+            if (ctx->buf[B_ACCH].ensure((size_t)nc * p->n_bins * 4)) return fail(MCQ_ENOMEM, "device allocation failed");
+            a.acc_hist = static_cast<uint32_t *>(ctx->buf[B_ACCH].p);
+        }
+        CUDA_TRY(cudaMemsetAsync(a.acc_hist, 0, (size_t)nc * p->n_bins * 4, s));
+    }
+
+    // ---- accept bitmap ----
+    const long long abits_words = ((long long)ns + 31) / 32;
+    if (p->accept_bits) {
+        a.abits_pitch = abits_words;
+        if (mem == MCQ_MEM_DEVICE) a.abits = p->accept_bits;
+        else {
+            if (ctx->buf[B_ABITS].ensure((size_t)nc * abits_words * 4 + 4)) return fail(MCQ_ENOMEM, "device allocation failed");
+            a.abits = static_cast<uint32_t *>(ctx->buf[B_ABITS].p);
+        }
+    }
+
+    // ---- statistics accumulators ----
+    unsigned long long *d_sum_e = nullptr, *d_sum_e2 = nullptr;
+    const size_t stat_elems = (size_t)p->n_groups * ((size_t)ns + 1);
+    if (want_stats) {
+        if (mem == MCQ_MEM_DEVICE) { d_sum_e = reinterpret_cast<unsigned long long *>(p->stat_sum_e); d_sum_e2 = reinterpret_cast<unsigned long long *>(p->stat_sum_e2); }
+        else {
+            if (ctx->buf[B_SUME].ensure(stat_elems * 8) || ctx->buf[B_SUME2].ensure(stat_elems * 8)) return fail(MCQ_ENOMEM, "device allocation failed");
+            d_sum_e = static_cast<unsigned long long *>(ctx->buf[B_SUME].p);
+            d_sum_e2 = static_cast<unsigned long long *>(ctx->buf[B_SUME2].p);
+        }
+        CUDA_TRY(cudaMemsetAsync(d_sum_e, 0, stat_elems * 8, s));
+        CUDA_TRY(cudaMemsetAsync(d_sum_e2, 0, stat_elems * 8, s));
+    }
+
+    // ---- history plan ----
+    int hkind = MCQ_HIST_NONE;
+    if (want_hist) hkind = p->hist_dtype;
+    else if (want_stats) hkind = e_max < 65536 ? MCQ_HIST_U16 : MCQ_HIST_I32;
+    const size_t esz = hkind == MCQ_HIST_U16 ? 2 : 4;
+    const bool direct = want_hist && mem == MCQ_MEM_DEVICE;  // kernel writes the caller's array itself
+    int chunk = ns > 0 ? ns : 1;
+    if (hkind != MCQ_HIST_NONE && !direct) {
+        if (p->chunk_steps > 0) chunk = p->chunk_steps;
+        else {
+            const size_t budget = (size_t)256 << 20;  // per buffer
+            size_t c = budget / ((size_t)nc * esz);
+            chunk = (int)std::min<size_t>(std::max<size_t>(c, 64), (size_t)std::max(ns, 1));
+        }
+    } else if (p->chunk_steps > 0) chunk = p->chunk_steps;
+    chunk = std::max(HBLK, chunk / HBLK * HBLK);
+    const long long chunk_pitch = (long long)chunk + 1;
+    if (hkind != MCQ_HIST_NONE && !direct) {
+        const size_t bytes = (size_t)nc * chunk_pitch * esz;
+        if (ctx->buf[B_HIST0].ensure(bytes)) return fail(MCQ_ENOMEM, "device allocation failed (history chunk)");
+        if (ns > chunk && ctx->buf[B_HIST1].ensure(bytes)) return fail(MCQ_ENOMEM, "device allocation failed (history chunk)");
+    }
+
+    // ---- the launches ----
+    std::vector<cudaEvent_t> ev;
+    cudaEvent_t buf_free[2] = {nullptr, nullptr}, chunk_done = nullptr;
+    if (want_hist && !direct) {
+        CUDA_TRY(cudaEventCreateWithFlags(&buf_free[0], cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&buf_free[1], cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&chunk_done, cudaEventDisableTiming));
+    }
+    int rc_loop = 0;
+    int ci = 0;
+    int t0 = 0;
+    do {
+        const int t1 = std::min(ns, t0 + chunk);
+        a.t_begin = t0; a.t_end = t1;
+        a.hist_kind = hkind;
+        if (hkind != MCQ_HIST_NONE) {
+            if (direct) { a.hist = p->energy_history; a.hist_pitch = p->hist_pitch; a.h_origin = 0; }
+            else {
+                a.hist = ctx->buf[(ci & 1) ? B_HIST1 : B_HIST0].p;
+                a.hist_pitch = chunk_pitch;
+                a.h_origin = t0 == 0 ? 0 : (long long)t0 + 1;
+                if (want_hist && ci >= 2) CUDA_TRY(cudaStreamWaitEvent(s, buf_free[ci & 1], 0));
+            }
+        }
+        a.bin_at_begin = 0;
+        if (p->n_bins > 0) {
+            int b = 0;
+            while (b + 1 < p->n_bins && p->bin_starts[b + 1] <= t0) ++b;
+            a.bin_at_begin = b;
+        }
+        cudaEvent_t e0, e1;
+        CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1));
+        ev.push_back(e0); ev.push_back(e1);
+        CUDA_TRY(cudaEventRecord(e0, s));
+        CUDA_TRY(launch_anneal(G, a, replay, grid, block, smem, s));
+        CUDA_TRY(cudaEventRecord(e1, s));
+        ++launches;
+        // first history column of this launch and how many columns it produced
+        const long long h0 = t0 == 0 ? 0 : (long long)t0 + 1;
+        const int n_cols = (int)((long long)t1 + 1 - h0);
+        if (want_stats && n_cols > 0) {
+            const void *hb = direct ? static_cast<const char *>(p->energy_history) + (size_t)h0 * esz : a.hist;
+            const long long hp = direct ? p->hist_pitch : chunk_pitch;
+            dim3 sg((n_cols + 127) / 128, std::max(1, std::min(64, nc / 256)));
+            if (hkind == MCQ_HIST_U16)
+                stats_kernel<uint16_t><<<sg, 128, 0, s>>>(static_cast<const uint16_t *>(hb), hp, n_cols, h0, nc, a.group, a.steps_done, d_sum_e, d_sum_e2, (long long)ns + 1);
+            else
+                stats_kernel<int><<<sg, 128, 0, s>>>(static_cast<const int *>(hb), hp, n_cols, h0, nc, a.group, a.steps_done, d_sum_e, d_sum_e2, (long long)ns + 1);
+            CUDA_TRY(cudaGetLastError());
+            ++launches;
+        }
+        if (want_hist && !direct && n_cols > 0) {
+            CUDA_TRY(cudaEventRecord(chunk_done, s));
+            CUDA_TRY(cudaStreamWaitEvent(ctx->copy_stream, chunk_done, 0));
+            CUDA_TRY(cudaMemcpy2DAsync(static_cast<char *>(p->energy_history) + (size_t)h0 * esz, (size_t)p->hist_pitch * esz,
+                                       a.hist, (size_t)chunk_pitch * esz, (size_t)n_cols * esz, nc, cudaMemcpyDeviceToHost,
+                                       ctx->copy_stream));
+            CUDA_TRY(cudaEventRecord(buf_free[ci & 1], ctx->copy_stream));
+        }
+        t0 = t1;
+        ++ci;
+    } while (t0 < ns);
+    (void)rc_loop;
+
+    // ---- outputs ----
+    if (int rc = copy_out(p->initial_energy, a.init_e, (size_t)nc * 4, mem, s)) return rc;
+    if (int rc = copy_out(p->final_energy, a.cur_e, (size_t)nc * 4, mem, s)) return rc;
+    if (int rc = copy_out(p->best_energy, a.best_e, (size_t)nc * 4, mem, s)) return rc;
+    if (int rc = copy_out(p->steps_to_best, a.best_step, (size_t)nc * 4, mem, s)) return rc;
+    if (int rc = copy_out(p->n_accepted, a.n_acc, (size_t)nc * 4, mem, s)) return rc;
+    if (int rc = copy_out(p->steps_done, a.steps_done, (size_t)nc * 4, mem, s)) return rc;
+    if (int rc = copy_out(p->n_near_threshold, a.near_cnt, (size_t)nc * 4, mem, s)) return rc;
+    if (int rc = copy_out(p->final_state, a.state, (size_t)nc * sbytes, mem, s)) return rc;
+    if (int rc = copy_out(p->best_state, a.best_state, (size_t)nc * sbytes, mem, s)) return rc;
+    if (mem == MCQ_MEM_HOST) {
+        if (p->n_bins > 0) CUDA_TRY(cudaMemcpyAsync(p->accept_hist, a.acc_hist, (size_t)nc * p->n_bins * 4, cudaMemcpyDeviceToHost, s));
+        if (p->accept_bits) CUDA_TRY(cudaMemcpyAsync(p->accept_bits, a.abits, (size_t)nc * abits_words * 4, cudaMemcpyDeviceToHost, s));
+        if (want_stats) {
+            CUDA_TRY(cudaMemcpyAsync(p->stat_sum_e, d_sum_e, stat_elems * 8, cudaMemcpyDeviceToHost, s));
+            CUDA_TRY(cudaMemcpyAsync(p->stat_sum_e2, d_sum_e2, stat_elems * 8, cudaMemcpyDeviceToHost, s));
+        }
+    }
+    uint32_t h_err = 0;
+    if (replay) CUDA_TRY(cudaMemcpyAsync(&h_err, a.replay_err, 4, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    if (want_hist && !direct) CUDA_TRY(cudaStreamSynchronize(ctx->copy_stream));
+    float ms_total = 0.f;
+    for (size_t i = 0; i + 1 < ev.size(); i += 2) {
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, ev[i], ev[i + 1]));
+        ms_total += ms;
+    }
+    for (auto e : ev) cudaEventDestroy(e);
+    if (buf_free[0]) { cudaEventDestroy(buf_free[0]); cudaEventDestroy(buf_free[1]); cudaEventDestroy(chunk_done); }
+    if (p->kernel_ms) *p->kernel_ms = ms_total;
+    if (p->gpu_launches) *p->gpu_launches = launches;
+    if (replay && h_err) return fail(MCQ_EREPLAY, "replayed stream contained an illegal proposal (occupied cell, same height or out of range)");
+    return 0;
+}
+
+}  // extern "C"

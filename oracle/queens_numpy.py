@@ -101,7 +101,7 @@ def _attack_flags(di, dj, dk, zi, zj, zk, with_column):
 
 def energy_of_cells(cells, with_column=True):
     """Number of unordered attacking pairs among ``cells[Q,3]`` (mcmc.py:134-169)."""
-    cells = np.asarray(cells)
+    cells = np.asarray(cells).astype(np.int64)      # unsigned inputs must not wrap in a - b
     if cells.shape[0] < 2:
         return 0
     a = cells[:, None, :]
@@ -136,8 +136,8 @@ def energy_full(cells):
 
 def conflicts_full(cells, q_idx, cell=None):
     """Queens other than ``q_idx`` attacking ``cell`` (default: its own cell); mcmc.py:185-226."""
-    cells = np.asarray(cells)
-    target = cells[q_idx] if cell is None else np.asarray(cell)
+    cells = np.asarray(cells).astype(np.int64)
+    target = cells[q_idx] if cell is None else np.asarray(cell).astype(np.int64)
     keep = np.arange(cells.shape[0]) != q_idx
     rest = cells[keep]
     if rest.shape[0] == 0:
@@ -151,7 +151,7 @@ def conflicts_full(cells, q_idx, cell=None):
 
 def conflicts_board(heights, i, j, k=None):
     """Queens outside column (i,j) attacking (i,j,k); mcmc_board.py:147-193."""
-    heights = np.asarray(heights)
+    heights = np.asarray(heights).astype(np.int64)
     if k is None:
         k = heights[i, j]
     cells = board_cells(heights)
