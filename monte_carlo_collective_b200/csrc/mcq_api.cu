@@ -629,7 +629,7 @@ int mcq_run(mcq_ctx *ctx, const mcq_run_params *p) {
     if (hkind != MCQ_HIST_NONE && !direct) {
         if (p->chunk_steps > 0) chunk = p->chunk_steps;
         else {
-            const size_t budget = (size_t)256 << 20;  // per buffer
+            const size_t budget = (size_t)1 << 30;  // per buffer
             size_t c = budget / ((size_t)nc * esz);
             chunk = (int)std::min<size_t>(std::max<size_t>(c, 64), (size_t)std::max(ns, 1));
         }

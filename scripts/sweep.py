@@ -1,0 +1,57 @@
+"""Throughput sweep over kernel geometry (development tool; writes gpurun_out/sweep.jsonl)."""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as ge  # noqa: E402
+
+ge.build()
+import monte_carlo_collective_b200 as mcq  # noqa: E402
+from monte_carlo_collective_b200 import schedules  # noqa: E402
+
+eng = mcq.Engine(0)
+os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+out = open(os.path.join(ROOT, "gpurun_out", "sweep.jsonl"), "a")
+LIN = {"type": "linear_annealing", "beta_start": 1.0, "beta_end": 3.0}
+
+
+def run(tag, mode, n, nc, ns, history="none", **kw):
+    import torch
+    betas = schedules.beta_table(LIN, ns)
+    tab = torch.from_numpy(schedules.to_device_table(betas)).cuda()
+    seeds = torch.arange(nc, dtype=torch.int64).cuda()
+    best = None
+    for _ in range(2):
+        t0 = time.time()
+        r = eng.run(mode, n, ns, seeds, None, beta_device_table=tab, history=history, device_buffers=True,
+                    want_states=False, **kw)
+        wall = time.time() - t0
+        pps = nc * ns / (r.kernel_ms * 1e-3)
+        if best is None or pps > best["pps"]:
+            best = dict(tag=tag, mode=mode, n=n, chains=nc, steps=ns, history=history, kernel_ms=r.kernel_ms,
+                        wall_ms=wall * 1e3, pps=pps, acc=float(r.n_accepted.float().mean()) / ns, **kw)
+    print(json.dumps(best), flush=True)
+    out.write(json.dumps(best) + "\n")
+    out.flush()
+
+
+which = sys.argv[1] if len(sys.argv) > 1 else "base"
+if which == "base":
+    for mode in ("full_3d", "board"):
+        for G in (4, 8, 16, 32):
+            run("G", mode, 12, 20480, 20000, lanes_per_chain=G)
+    for hist in ("full", "stats"):
+        run("hist", "full_3d", 12, 20480, 20000, history=hist, lanes_per_chain=8)
+    for mode in ("full_3d", "board"):
+        for n in (8, 15, 20):
+            run("N", mode, n, 8192, 10000)
+    run("N", "board", 64, 1184, 2000)
+elif which == "occ":
+    for G in (4, 8, 16):
+        for m in (8, 16, 24, 32, 40, 48):
+            run("occ", "full_3d", 12, 148 * m, 20000, lanes_per_chain=G, max_chains_per_sm=m)
