@@ -54,6 +54,11 @@ extern "C" {
 #define MCQ_HIST_U16 1 /* legal when 13*Q*(N-1)/2 < 65536 */
 #define MCQ_HIST_I32 2
 
+/* delta-E data structure / kernel */
+#define MCQ_ALGO_AUTO 0   /* conflict table when its uint8 entries suffice, else line counters */
+#define MCQ_ALGO_LINES 1  /* per-line occupancy counters, `lanes_per_chain` lanes per chain (anneal.cuh) */
+#define MCQ_ALGO_TABLE 2  /* per-cell conflict table, one warp per chain, speculative rounds (spec.cuh) */
+
 /* error codes */
 #define MCQ_OK 0
 #define MCQ_EINVAL -1   /* bad argument (the Python shim raises ValueError) */
@@ -126,6 +131,7 @@ typedef struct mcq_run_params {
     int32_t warps_per_cta;
     int32_t chunk_steps;     /* steps per launch when the history is streamed */
     int32_t max_chains_per_sm;
+    int32_t algo;            /* MCQ_ALGO_*; a non-zero lanes_per_chain with AUTO selects LINES */
     void *stream;            /* cudaStream_t, or NULL for the context's own stream */
 } mcq_run_params;
 

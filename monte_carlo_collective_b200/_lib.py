@@ -18,6 +18,7 @@ MEM_HOST, MEM_DEVICE = 0, 1
 HIST_NONE, HIST_U16, HIST_I32 = 0, 1, 2
 OK, EINVAL, ECUDA, ENOMEM, EREPLAY = 0, -1, -2, -3, -4
 ABI_VERSION = 1
+ALGO_AUTO, ALGO_LINES, ALGO_TABLE = 0, 1, 2
 
 
 class McqError(RuntimeError):
@@ -72,6 +73,7 @@ class RunParams(C.Structure):
         ("warps_per_cta", C.c_int32),
         ("chunk_steps", C.c_int32),
         ("max_chains_per_sm", C.c_int32),
+        ("algo", C.c_int32),
         ("stream", C.c_void_p),
     ]
 

@@ -45,6 +45,15 @@ struct Layout {
     int pb;         // packets produced per batch = min(G, 8)
 };
 
+// byte offsets inside one chain's slab for the conflict-table kernel (spec.cuh)
+struct SLayout {
+    int tbl;        // table bytes (N^3 rounded up to 4)
+    int off_state;  // board: heights; full_3d: packed queen positions (uint16)
+    int off_occ;    // full_3d: occupancy bitset
+    int stride;     // slab size, multiple of 16
+    int rounds;     // ceil(families * N / 32): candidate rounds of a table update
+};
+
 struct KArgs {
     int full;  // 0 board, 1 full_3d
     int N, Q;
@@ -53,6 +62,7 @@ struct KArgs {
     int t_begin, t_end;   // this launch covers steps [t_begin, t_end)
     int patience;         // < 0: none
     Layout lay;
+    SLayout sl;
     int4 coef[NFAM];      // idx = x*i + y*j + z*k + w  (w includes the family base)
     // per-chain inputs
     const unsigned long long *seeds;

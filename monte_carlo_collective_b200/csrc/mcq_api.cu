@@ -14,6 +14,7 @@
 
 #include "../../include/mcq.h"
 #include "anneal.cuh"
+#include "spec.cuh"
 
 namespace mcq {
 
@@ -82,6 +83,21 @@ static Layout make_layout(int full, int N, int Q, int G) {
     L.stride = round_up(L.off_hst + HBLK * 4, 16);
     return L;
 }
+
+static SLayout make_spec_layout(int full, int N, int Q) {
+    SLayout L;
+    L.tbl = round_up(N * N * N, 4);
+    L.off_state = L.tbl;
+    const int state_b = full ? Q * 2 : N * N;
+    L.off_occ = round_up(L.off_state + state_b, 4);
+    const int occ_b = full ? (N * N * N + 31) / 32 * 4 : 0;
+    L.stride = round_up(L.off_occ + occ_b, 16);
+    L.rounds = ((full ? NFAM : NFAM - 1) * N + 31) / 32;
+    return L;
+}
+
+// uint8 table entries hold at most 13*N (full_3d) / 12*N (board)
+static inline bool spec_eligible(int full, int N) { return (full ? 13 : 12) * N <= 255; }
 
 static inline int state_bytes_of(int mode, int n, int q) { return mode == MCQ_MODE_FULL3D ? 3 * q : n * n; }
 
@@ -266,6 +282,20 @@ template <int G>
 static cudaError_t launch_g(const KArgs &a, bool replay, int grid, int block, size_t smem, cudaStream_t s) {
     if (a.full) return replay ? launch_one<G, true, true>(a, grid, block, smem, s) : launch_one<G, true, false>(a, grid, block, smem, s);
     return replay ? launch_one<G, false, true>(a, grid, block, smem, s) : launch_one<G, false, false>(a, grid, block, smem, s);
+}
+
+template <bool FULL, bool REPLAY>
+static cudaError_t launch_spec_one(const KArgs &a, int grid, int block, size_t smem, cudaStream_t s) {
+    auto k = spec_kernel<FULL, REPLAY>;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    k<<<grid, block, smem, s>>>(a);
+    return cudaGetLastError();
+}
+
+static cudaError_t launch_spec(const KArgs &a, bool replay, int grid, int block, size_t smem, cudaStream_t s) {
+    if (a.full) return replay ? launch_spec_one<true, true>(a, grid, block, smem, s) : launch_spec_one<true, false>(a, grid, block, smem, s);
+    return replay ? launch_spec_one<false, true>(a, grid, block, smem, s) : launch_spec_one<false, false>(a, grid, block, smem, s);
 }
 
 static cudaError_t launch_anneal(int G, const KArgs &a, bool replay, int grid, int block, size_t smem, cudaStream_t s) {
@@ -489,6 +519,9 @@ int mcq_run(mcq_ctx *ctx, const mcq_run_params *p) {
     const size_t smem_sm = ctx->prop.sharedMemPerMultiprocessor;
     int G = p->lanes_per_chain;
     if (G != 0 && G != 4 && G != 8 && G != 16 && G != 32) return fail(MCQ_EINVAL, "lanes_per_chain must be 0, 4, 8, 16 or 32");
+    if (p->algo < MCQ_ALGO_AUTO || p->algo > MCQ_ALGO_TABLE) return fail(MCQ_EINVAL, "unknown algo");
+    if (p->algo == MCQ_ALGO_TABLE && !spec_eligible(full, p->n)) return fail(MCQ_EINVAL, "MCQ_ALGO_TABLE needs 13*N <= 255 (full_3d) or 12*N <= 255 (board)");
+    const bool use_spec = p->algo == MCQ_ALGO_TABLE || (p->algo == MCQ_ALGO_AUTO && G == 0 && spec_eligible(full, p->n));
     if (G == 0) {
         G = 8;
         while (G < 32 && (size_t)make_layout(full, p->n, p->q, G).stride * (32 / G) > smem_block) G *= 2;
@@ -508,11 +541,25 @@ int mcq_run(mcq_ctx *ctx, const mcq_run_params *p) {
         if (ctas * cpc_w > best_chains) { best_chains = ctas * cpc_w; best_w = w; best_ctas = ctas; }
     }
     if (best_chains == 0) return fail(MCQ_ENOMEM, "requested warps_per_cta does not fit in shared memory");
-    const int cpc = best_w * 32 / G;
-    const int block = best_w * 32;
-    const int grid = (nc + cpc - 1) / cpc;
+    int cpc = best_w * 32 / G;
+    int block = best_w * 32;
+    int grid = (nc + cpc - 1) / cpc;
     size_t smem = (size_t)cpc * lay.stride;
-    {   // cap residency (explicit limit, or balance the waves) by padding the shared-memory request
+    const SLayout sl = make_spec_layout(full, p->n, p->q);
+    if (use_spec) {   // one warp per chain; the register file bounds residency, not shared memory
+        if (wpc > 4) return fail(MCQ_EINVAL, "the conflict-table kernel runs at most 4 warps per CTA");
+        const int w = wpc ? wpc : 4;
+        cpc = w;
+        block = w * 32;
+        grid = (nc + cpc - 1) / cpc;
+        smem = (size_t)sl.rounds * 128 + (size_t)cpc * sl.stride;
+        if (smem > smem_block) return fail(MCQ_ENOMEM, "conflict-table slab does not fit in shared memory; lower warps_per_cta");
+        if (p->max_chains_per_sm > 0) {
+            const int ctas = std::max(1, p->max_chains_per_sm / cpc);
+            size_t pad = std::min(smem_sm / ctas - 1024, smem_block) & ~(size_t)15;
+            smem = std::max(smem, pad);
+        }
+    } else {   // cap residency (explicit limit, or balance the waves) by padding the shared-memory request
         int ctas = best_ctas;
         const int sms = ctx->prop.multiProcessorCount;
         if (p->max_chains_per_sm > 0) ctas = std::max(1, std::min(ctas, p->max_chains_per_sm / cpc));
@@ -535,6 +582,7 @@ int mcq_run(mcq_ctx *ctx, const mcq_run_params *p) {
     a.full = full; a.N = p->n; a.Q = p->q; a.n_chains = nc; a.n_steps = ns;
     a.patience = (!full && p->early_stop_patience >= 0) ? p->early_stop_patience : -1;
     a.lay = lay;
+    a.sl = sl;
     make_coefs(full, p->n, a.coef);
     a.state_bytes = sbytes;
     void *d = nullptr;
@@ -603,6 +651,7 @@ int mcq_run(mcq_ctx *ctx, const mcq_run_params *p) {
             if (ctx->buf[B_ABITS].ensure((size_t)nc * abits_words * 4 + 4)) return fail(MCQ_ENOMEM, "device allocation failed");
             a.abits = static_cast<uint32_t *>(ctx->buf[B_ABITS].p);
         }
+        CUDA_TRY(cudaMemsetAsync(a.abits, 0, (size_t)nc * abits_words * 4, s));   // the table kernel stores non-zero words only
     }
 
     // ---- statistics accumulators ----
@@ -668,15 +717,17 @@ int mcq_run(mcq_ctx *ctx, const mcq_run_params *p) {
         }
         a.bin_at_begin = 0;
         if (p->n_bins > 0) {
+            // the bin that was still open when the previous launch ended (the kernels close a bin
+            // when they reach its right edge, which may be the first step of this launch)
             int b = 0;
-            while (b + 1 < p->n_bins && p->bin_starts[b + 1] <= t0) ++b;
+            if (t0 > 0) while (b + 1 < p->n_bins && p->bin_starts[b + 1] <= t0 - 1) ++b;
             a.bin_at_begin = b;
         }
         cudaEvent_t e0, e1;
         CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1));
         ev.push_back(e0); ev.push_back(e1);
         CUDA_TRY(cudaEventRecord(e0, s));
-        CUDA_TRY(launch_anneal(G, a, replay, grid, block, smem, s));
+        CUDA_TRY(use_spec ? launch_spec(a, replay, grid, block, smem, s) : launch_anneal(G, a, replay, grid, block, smem, s));
         CUDA_TRY(cudaEventRecord(e1, s));
         ++launches;
         // first history column of this launch and how many columns it produced

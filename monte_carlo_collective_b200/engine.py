@@ -184,7 +184,7 @@ class Engine:
             init_states=None, history="full", hist_dtype=None, accept_bits=False, n_bins=0,
             early_stop_patience=None, replay=None, want_states=True, device_buffers=False,
             beta_device_table=None, lanes_per_chain=0, warps_per_cta=0, chunk_steps=0, max_chains_per_sm=0,
-            stream=None, out=None) -> RunResult:
+            algo=0, stream=None, out=None) -> RunResult:
         """Run ``len(seeds)`` independent chains.
 
         seeds   uint64 per chain (the Philox key; reference: ``base_seed + r``, experiments.py:508)
@@ -299,6 +299,7 @@ class Engine:
         p.gpu_launches = C.addressof(launches)
         p.lanes_per_chain, p.warps_per_cta = lanes_per_chain, warps_per_cta
         p.chunk_steps, p.max_chains_per_sm = chunk_steps, max_chains_per_sm
+        p.algo = {"auto": 0, "lines": 1, "table": 2}.get(algo, algo)
         p.stream = stream
         _lib.check(self._lib.mcq_run(self._h, C.byref(p)))
         res.kernel_ms, res.gpu_launches = float(ms.value), int(launches.value)

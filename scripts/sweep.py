@@ -51,6 +51,16 @@ if which == "base":
         for n in (8, 15, 20):
             run("N", mode, n, 8192, 10000)
     run("N", "board", 64, 1184, 2000)
+elif which == "table":
+    for mode in ("full_3d", "board"):
+        for w in (1, 2, 4):
+            run("table", mode, 12, 20480, 20000, algo="table", warps_per_cta=w)
+    run("table", "full_3d", 12, 20480, 200000, algo="table")
+    run("table", "full_3d", 12, 20480, 20000, algo="table", history="stats")
+    for mode in ("full_3d", "board"):
+        for n in (8, 15, 19):
+            run("tableN", mode, n, 8192, 10000, algo="table")
+    run("tableN", "board", 20, 8192, 10000, algo="table")
 elif which == "occ":
     for G in (4, 8, 16):
         for m in (8, 16, 24, 32, 40, 48):

@@ -24,7 +24,7 @@ def _run(engine, g, lanes, **kw):
                       lanes_per_chain=lanes, **kw)
 
 
-@pytest.mark.parametrize("lanes", [4, 8, 16, 32])
+@pytest.mark.parametrize("lanes", [0, 4, 8, 16, 32])  # 0 = conflict-table kernel when eligible
 @pytest.mark.parametrize("path", replay_files(), ids=lambda p: os.path.basename(p)[7:-4])
 def test_replay_bit_exact(engine, path, lanes):
     g = np.load(path)
@@ -53,17 +53,18 @@ def test_replay_batch_and_chunked_launches(engine):
         g = np.load(path)
         mode, n, ns = str(g["mode"]), int(g["n"]), int(g["n_steps"])
         reps = 5
-        r = engine.run(mode, n, ns, np.arange(reps, dtype=np.uint64), g["betas"],
-                       init_states=np.repeat(g["init_state"][None], reps, 0).astype(np.uint8),
-                       history="full", accept_bits=True, chunk_steps=352,
-                       replay={"moves": np.repeat(g["moves"][None], reps, 0),
-                               "uniforms": np.repeat(g["uniforms"][None], reps, 0)})
-        assert r.gpu_launches >= ns // 352
-        for c in range(reps):
-            assert r.energy_history[c].tolist() == g["history"].tolist()
-            assert r.accepted_mask(c).astype(np.uint8).tolist() == g["accepted"].tolist()
-            assert int(r.steps_to_best[c]) == int(g["steps_to_best"])
-            assert r.best_state[c].astype(np.int64).tolist() == g["best_state"].tolist()
+        for algo in ("table", "lines"):
+            r = engine.run(mode, n, ns, np.arange(reps, dtype=np.uint64), g["betas"],
+                           init_states=np.repeat(g["init_state"][None], reps, 0).astype(np.uint8),
+                           history="full", accept_bits=True, chunk_steps=352, algo=algo,
+                           replay={"moves": np.repeat(g["moves"][None], reps, 0),
+                                   "uniforms": np.repeat(g["uniforms"][None], reps, 0)})
+            assert r.gpu_launches >= ns // 352
+            for c in range(reps):
+                assert r.energy_history[c].tolist() == g["history"].tolist()
+                assert r.accepted_mask(c).astype(np.uint8).tolist() == g["accepted"].tolist()
+                assert int(r.steps_to_best[c]) == int(g["steps_to_best"])
+                assert r.best_state[c].astype(np.int64).tolist() == g["best_state"].tolist()
 
 
 def test_replay_rejects_illegal_stream(engine):
