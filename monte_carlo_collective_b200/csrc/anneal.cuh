@@ -47,11 +47,12 @@ struct Layout {
 
 // byte offsets inside one chain's slab for the conflict-table kernel (spec.cuh)
 struct SLayout {
-    int tbl;        // table bytes (N^3 rounded up to 4)
+    int tbl;        // table bytes (N^3 + 1 scratch byte, rounded up to 4)
     int off_state;  // board: heights; full_3d: packed queen positions (uint16)
     int off_occ;    // full_3d: occupancy bitset
     int stride;     // slab size, multiple of 16
-    int rounds;     // ceil(families * N / 32): candidate rounds of a table update
+    int nbr_len;    // neighbour-row length: families*(N-1) rounded up to 32
+    int rounds;     // nbr_len / 32
 };
 
 struct KArgs {
@@ -91,6 +92,7 @@ struct KArgs {
     int n_bins;
     int bin_at_begin;      // bin containing t_begin
     uint32_t *acc_hist;    // [n_chains][n_bins]
+    const uint16_t *nbr;   // conflict-table kernel: neighbour lists [N^3][sl.nbr_len]
 };
 
 __device__ __forceinline__ int line_index(const int4 c, int i, int j, int k) {

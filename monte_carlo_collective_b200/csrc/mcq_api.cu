@@ -9,6 +9,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -86,13 +87,14 @@ static Layout make_layout(int full, int N, int Q, int G) {
 
 static SLayout make_spec_layout(int full, int N, int Q) {
     SLayout L;
-    L.tbl = round_up(N * N * N, 4);
+    L.tbl = round_up(N * N * N + 1, 4);
     L.off_state = L.tbl;
     const int state_b = full ? Q * 2 : N * N;
     L.off_occ = round_up(L.off_state + state_b, 4);
     const int occ_b = full ? (N * N * N + 31) / 32 * 4 : 0;
     L.stride = round_up(L.off_occ + occ_b, 16);
-    L.rounds = ((full ? NFAM : NFAM - 1) * N + 31) / 32;
+    L.nbr_len = round_up((full ? NFAM : NFAM - 1) * (N - 1), 32);
+    L.rounds = L.nbr_len / 32;
     return L;
 }
 
@@ -265,6 +267,7 @@ struct mcq_ctx {
     cudaStream_t copy_stream;
     cudaDeviceProp prop;
     mcq::DevBuf buf[mcq::B_NBUF];
+    std::map<int, mcq::DevBuf> nbr;   // neighbour lists per (mode, N), built on first use
 };
 
 namespace mcq {
@@ -374,6 +377,7 @@ int mcq_destroy(mcq_ctx *ctx) {
     if (!ctx) return 0;
     cudaSetDevice(ctx->device);
     for (auto &b : ctx->buf) b.release();
+    for (auto &kv : ctx->nbr) kv.second.release();
     cudaStreamDestroy(ctx->stream);
     cudaStreamDestroy(ctx->copy_stream);
     delete ctx;
@@ -552,7 +556,7 @@ int mcq_run(mcq_ctx *ctx, const mcq_run_params *p) {
         cpc = w;
         block = w * 32;
         grid = (nc + cpc - 1) / cpc;
-        smem = (size_t)sl.rounds * 128 + (size_t)cpc * sl.stride;
+        smem = (size_t)cpc * sl.stride;
         if (smem > smem_block) return fail(MCQ_ENOMEM, "conflict-table slab does not fit in shared memory; lower warps_per_cta");
         if (p->max_chains_per_sm > 0) {
             const int ctas = std::max(1, p->max_chains_per_sm / cpc);
@@ -583,6 +587,17 @@ int mcq_run(mcq_ctx *ctx, const mcq_run_params *p) {
     a.patience = (!full && p->early_stop_patience >= 0) ? p->early_stop_patience : -1;
     a.lay = lay;
     a.sl = sl;
+    if (use_spec) {
+        DevBuf &nb = ctx->nbr[full * 256 + p->n];
+        if (!nb.p) {
+            const int cells = p->n * p->n * p->n;
+            if (nb.ensure((size_t)cells * sl.nbr_len * 2)) return fail(MCQ_ENOMEM, "device allocation failed (neighbour lists)");
+            build_neighbours_kernel<<<(cells + 127) / 128, 128, 0, s>>>(full, p->n, sl.nbr_len, static_cast<uint16_t *>(nb.p));
+            CUDA_TRY(cudaGetLastError());
+            ++launches;
+        }
+        a.nbr = static_cast<const uint16_t *>(nb.p);
+    }
     make_coefs(full, p->n, a.coef);
     a.state_bytes = sbytes;
     void *d = nullptr;

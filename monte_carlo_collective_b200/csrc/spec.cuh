@@ -45,27 +45,44 @@ __device__ __forceinline__ void family_dir(int f, int &dx, int &dy, int &dz) {
     dz = (int)((PZ >> (2 * f)) & 3) - 1;
 }
 
-// Add `delta` to T at every cell != (ax,ay,az) on the attack lines through it.  Candidate (f,u) of
-// the slot table: the cell of line f whose primary coordinate equals u.  All lanes must call.
-__device__ __forceinline__ void table_lines_add(uint8_t *T, const uint32_t *slots, int rounds, int lane, int N,
-                                                int ax, int ay, int az, int delta) {
-    for (int r = 0; r < rounds; ++r) {
-        const uint32_t sw = slots[r * 32 + lane];
-        const int dx = (int)((sw >> 1) & 3) - 1, dy = (int)((sw >> 3) & 3) - 1, dz = (int)((sw >> 5) & 3) - 1;
-        const int p = (sw >> 7) & 3, u = (sw >> 9) & 63;
-        const int tau = u - (p == 0 ? ax : p == 1 ? ay : az);
-        const int x = ax + tau * dx, y = ay + tau * dy, z = az + tau * dz;
-        const bool ok = (sw & 1u) && tau != 0 && (unsigned)x < (unsigned)N && (unsigned)y < (unsigned)N &&
-                        (unsigned)z < (unsigned)N;
-        if (ok) {
-            const int c = (x * N + y) * N + z;
-            T[c] = (uint8_t)(T[c] + delta);
+// Neighbour lists, shared by every chain of a launch (geometry only, L2-resident): row `cell` holds
+// the ids of all cells on the attack lines through `cell` (itself excluded), padded to a multiple
+// of 32 with the id N^3, a scratch byte at the end of every table, so updates need no predicate.
+__global__ void build_neighbours_kernel(int full, int N, int L, uint16_t *nbr) {
+    const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cell >= N * N * N) return;
+    const int x = cell / (N * N), y = (cell / N) % N, z = cell % N;
+    uint16_t *row = nbr + (size_t)cell * L;
+    int n = 0;
+    for (int f = full ? 0 : 1; f < NFAM; ++f) {
+        int dx, dy, dz;
+        family_dir(f, dx, dy, dz);
+        for (int tau = -(N - 1); tau <= N - 1; ++tau) {
+            if (tau == 0) continue;
+            const int u = x + tau * dx, v = y + tau * dy, w = z + tau * dz;
+            if ((unsigned)u < (unsigned)N && (unsigned)v < (unsigned)N && (unsigned)w < (unsigned)N)
+                row[n++] = (uint16_t)((u * N + v) * N + w);
         }
     }
+    for (; n < L; ++n) row[n] = (uint16_t)(N * N * N);
+}
+
+constexpr int MAX_NBR_ROUNDS = 8;   // 13*(N-1) <= 256 for every N the uint8 table admits
+
+// T[c] += delta for every cell c on the attack lines through one cell (its neighbour row).
+// All lanes must call; `nr` = row length / 32.
+__device__ __forceinline__ void table_lines_add(uint8_t *T, const uint16_t *row, int nr, int lane, int delta) {
+    int c[MAX_NBR_ROUNDS];
+#pragma unroll
+    for (int r = 0; r < MAX_NBR_ROUNDS; ++r)
+        if (r < nr) c[r] = __ldg(row + r * 32 + lane);
+#pragma unroll
+    for (int r = 0; r < MAX_NBR_ROUNDS; ++r)
+        if (r < nr) T[c[r]] = (uint8_t)(T[c[r]] + delta);
 }
 
 template <bool FULL, bool REPLAY>
-__global__ void __launch_bounds__(128, 4) spec_kernel(const __grid_constant__ KArgs a) {
+__global__ void __launch_bounds__(128, 8) spec_kernel(const __grid_constant__ KArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     constexpr unsigned FULLMASK = 0xffffffffu;
     constexpr int NF = FULL ? NFAM : NFAM - 1;
@@ -73,24 +90,10 @@ __global__ void __launch_bounds__(128, 4) spec_kernel(const __grid_constant__ KA
     const int chain = blockIdx.x * (blockDim.x >> 5) + wid;
     const int N = a.N, rounds = a.sl.rounds;
 
-    // ---- slot table, shared by the CTA: slot s -> (family, primary coordinate) ----
-    uint32_t *slots = reinterpret_cast<uint32_t *>(smem);
-    for (int s = threadIdx.x; s < rounds * 32; s += blockDim.x) {
-        const int f = s / N, u = s - f * N;
-        uint32_t sw = 0u;
-        if (f < NF) {
-            int dx, dy, dz;
-            family_dir(FULL ? f : f + 1, dx, dy, dz);
-            const int p = dx ? 0 : dy ? 1 : 2;
-            sw = 1u | ((uint32_t)(dx + 1) << 1) | ((uint32_t)(dy + 1) << 3) | ((uint32_t)(dz + 1) << 5) | ((uint32_t)p << 7) |
-                 ((uint32_t)u << 9);
-        }
-        slots[s] = sw;
-    }
-    __syncthreads();
     if (chain >= a.n_chains) return;
+    const int L = a.sl.nbr_len;
 
-    unsigned char *S = smem + rounds * 128 + (size_t)wid * a.sl.stride;
+    unsigned char *S = smem + (size_t)wid * a.sl.stride;
     uint8_t *T = S;
     unsigned char *st = S + a.sl.off_state;
     uint32_t *occ = reinterpret_cast<uint32_t *>(S + a.sl.off_occ);
@@ -114,8 +117,9 @@ __global__ void __launch_bounds__(128, 4) spec_kernel(const __grid_constant__ KA
         int i, j, k;
         if (FULL) unpack_pos(0, load_pos(st, 0, qi), i, j, k);
         else { i = qi / N; j = qi - i * N; k = st[qi]; }
-        table_lines_add(T, slots, rounds, lane, N, i, j, k, 1);
-        if (lane == 0) { const int c = (i * N + j) * N + k; T[c] = (uint8_t)(T[c] + NF); }
+        const int c = (i * N + j) * N + k;
+        table_lines_add(T, a.nbr + (size_t)c * L, rounds, lane, 1);
+        if (lane == 0) T[c] = (uint8_t)(T[c] + NF);
         __syncwarp();
     }
     int E;
@@ -308,10 +312,10 @@ __global__ void __launch_bounds__(128, 4) spec_kernel(const __grid_constant__ KA
             const int ai = wc0 & 255, aj = (wc0 >> 8) & 255, ak = wc0 >> 16;
             const int bi = wc1 & 255, bj = (wc1 >> 8) & 255, bk = wc1 >> 16;
             const int ca = (ai * N + aj) * N + ak, cbn = (bi * N + bj) * N + bk;
-            table_lines_add(T, slots, rounds, lane, N, ai, aj, ak, -1);
+            table_lines_add(T, a.nbr + (size_t)ca * L, rounds, lane, -1);
             if (lane == 0) T[ca] = (uint8_t)(T[ca] - NF);
             __syncwarp();
-            table_lines_add(T, slots, rounds, lane, N, bi, bj, bk, +1);
+            table_lines_add(T, a.nbr + (size_t)cbn * L, rounds, lane, +1);
             if (lane == 0) {
                 T[cbn] = (uint8_t)(T[cbn] + NF);
                 if (FULL) {
