@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmcq.so")
+LIB_PATH = os.environ.get("MCQ_LIB_PATH") or os.path.join(_HERE, "libmcq.so")
 
 MODE_BOARD, MODE_FULL3D = 0, 1
 INIT_RANDOM, INIT_LATIN, INIT_KLARNER, INIT_EXPLICIT = 0, 1, 2, 3

@@ -48,11 +48,14 @@ struct Layout {
 // byte offsets inside one chain's slab for the conflict-table kernel (spec.cuh)
 struct SLayout {
     int tbl;        // table bytes (N^3 + 1 scratch byte, rounded up to 4)
-    int off_state;  // board: heights; full_3d: packed queen positions (uint16)
+    int off_state;  // board: heights; full_3d: uint32 per queen = cell id | wide id << 16
     int off_occ;    // full_3d: occupancy bitset
+    int off_rec;    // lane-0 scalars (RecSlot)
     int stride;     // slab size, multiple of 16
     int nbr_len;    // neighbour-row length: families*(N-1) rounded up to 32
     int rounds;     // nbr_len / 32
+    int off_wide;   // CTA-shared geometry (full_3d): [lut bits | wide ids]; byte offset of the wide ids
+    int cta_bytes;  // bytes of CTA-shared geometry in front of the slabs (0 in board mode)
 };
 
 struct KArgs {
@@ -93,6 +96,7 @@ struct KArgs {
     int bin_at_begin;      // bin containing t_begin
     uint32_t *acc_hist;    // [n_chains][n_bins]
     const uint16_t *nbr;   // conflict-table kernel: neighbour lists [N^3][sl.nbr_len]
+    const uint32_t *geo;   // conflict-table kernel, full_3d: shared-line bits then wide ids (sl.cta_bytes)
 };
 
 __device__ __forceinline__ int line_index(const int4 c, int i, int j, int k) {

@@ -89,12 +89,17 @@ static SLayout make_spec_layout(int full, int N, int Q) {
     SLayout L;
     L.tbl = round_up(N * N * N + 1, 4);
     L.off_state = L.tbl;
-    const int state_b = full ? Q * 2 : N * N;
+    const int state_b = full ? Q * 4 : N * N;
     L.off_occ = round_up(L.off_state + state_b, 4);
     const int occ_b = full ? (N * N * N + 31) / 32 * 4 : 0;
-    L.stride = round_up(L.off_occ + occ_b, 16);
+    L.off_rec = L.off_occ + occ_b;
+    L.stride = round_up(L.off_rec + 8 * 4, 16);
     L.nbr_len = round_up((full ? NFAM : NFAM - 1) * (N - 1), 32);
     L.rounds = L.nbr_len / 32;
+    const int W = 2 * N - 1;
+    const int lut_bytes = (W * W * W + 31) / 32 * 4;
+    L.off_wide = full ? lut_bytes : 0;
+    L.cta_bytes = full ? round_up(lut_bytes + N * N * N * 2, 16) : 0;
     return L;
 }
 
@@ -268,6 +273,7 @@ struct mcq_ctx {
     cudaDeviceProp prop;
     mcq::DevBuf buf[mcq::B_NBUF];
     std::map<int, mcq::DevBuf> nbr;   // neighbour lists per (mode, N), built on first use
+    std::map<int, mcq::DevBuf> geo;   // shared-line bits + wide ids per N (full_3d)
 };
 
 namespace mcq {
@@ -287,9 +293,9 @@ static cudaError_t launch_g(const KArgs &a, bool replay, int grid, int block, si
     return replay ? launch_one<G, false, true>(a, grid, block, smem, s) : launch_one<G, false, false>(a, grid, block, smem, s);
 }
 
-template <bool FULL, bool REPLAY>
+template <bool FULL, bool REPLAY, bool EARLY>
 static cudaError_t launch_spec_one(const KArgs &a, int grid, int block, size_t smem, cudaStream_t s) {
-    auto k = spec_kernel<FULL, REPLAY>;
+    auto k = spec_kernel<FULL, REPLAY, EARLY>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     k<<<grid, block, smem, s>>>(a);
@@ -297,8 +303,9 @@ static cudaError_t launch_spec_one(const KArgs &a, int grid, int block, size_t s
 }
 
 static cudaError_t launch_spec(const KArgs &a, bool replay, int grid, int block, size_t smem, cudaStream_t s) {
-    if (a.full) return replay ? launch_spec_one<true, true>(a, grid, block, smem, s) : launch_spec_one<true, false>(a, grid, block, smem, s);
-    return replay ? launch_spec_one<false, true>(a, grid, block, smem, s) : launch_spec_one<false, false>(a, grid, block, smem, s);
+    if (a.full) return replay ? launch_spec_one<true, true, false>(a, grid, block, smem, s) : launch_spec_one<true, false, false>(a, grid, block, smem, s);
+    if (a.patience >= 0) return replay ? launch_spec_one<false, true, true>(a, grid, block, smem, s) : launch_spec_one<false, false, true>(a, grid, block, smem, s);
+    return replay ? launch_spec_one<false, true, false>(a, grid, block, smem, s) : launch_spec_one<false, false, false>(a, grid, block, smem, s);
 }
 
 static cudaError_t launch_anneal(int G, const KArgs &a, bool replay, int grid, int block, size_t smem, cudaStream_t s) {
@@ -378,6 +385,7 @@ int mcq_destroy(mcq_ctx *ctx) {
     cudaSetDevice(ctx->device);
     for (auto &b : ctx->buf) b.release();
     for (auto &kv : ctx->nbr) kv.second.release();
+    for (auto &kv : ctx->geo) kv.second.release();
     cudaStreamDestroy(ctx->stream);
     cudaStreamDestroy(ctx->copy_stream);
     delete ctx;
@@ -556,7 +564,7 @@ int mcq_run(mcq_ctx *ctx, const mcq_run_params *p) {
         cpc = w;
         block = w * 32;
         grid = (nc + cpc - 1) / cpc;
-        smem = (size_t)cpc * sl.stride;
+        smem = (size_t)sl.cta_bytes + (size_t)cpc * sl.stride;
         if (smem > smem_block) return fail(MCQ_ENOMEM, "conflict-table slab does not fit in shared memory; lower warps_per_cta");
         if (p->max_chains_per_sm > 0) {
             const int ctas = std::max(1, p->max_chains_per_sm / cpc);
@@ -597,6 +605,21 @@ int mcq_run(mcq_ctx *ctx, const mcq_run_params *p) {
             ++launches;
         }
         a.nbr = static_cast<const uint16_t *>(nb.p);
+        if (full) {
+            DevBuf &gb = ctx->geo[p->n];
+            if (!gb.p) {
+                const int cells = p->n * p->n * p->n;
+                if (gb.ensure((size_t)sl.cta_bytes)) return fail(MCQ_ENOMEM, "device allocation failed (geometry tables)");
+                CUDA_TRY(cudaMemsetAsync(gb.p, 0, (size_t)sl.cta_bytes, s));
+                const int lut_words = sl.off_wide / 4;
+                const int n = std::max(cells, lut_words);
+                build_wide_lut_kernel<<<(n + 127) / 128, 128, 0, s>>>(p->n, reinterpret_cast<uint16_t *>(static_cast<char *>(gb.p) + sl.off_wide),
+                                                                     static_cast<uint32_t *>(gb.p), lut_words);
+                CUDA_TRY(cudaGetLastError());
+                ++launches;
+            }
+            a.geo = static_cast<const uint32_t *>(gb.p);
+        }
     }
     make_coefs(full, p->n, a.coef);
     a.state_bytes = sbytes;

@@ -15,9 +15,13 @@
 //     conflicts_for_queen / conflicts_for_position (mcmc.py:185-226, mcmc_board.py:147-193) count,
 //     plus 13 (12) for a queen standing on the cell itself:
 //         conflicts(old) = T[old] - 13,   conflicts(new) = T[new] - [old and new share a line]
-//     The table is maintained on accept only: -1 along the 13 lines through the old cell, +1 along
-//     those through the new one (all 32 lanes cooperate, 13*N candidate cells per phase).
-//   * per-chain shared memory is N^3 + state bytes (2.2 KB at N=12), so the register file, not
+//     "old and new share a line" depends on the coordinate differences only and is one bit of a
+//     (2N-1)^3-bit table.  T is maintained on accept only: -1 on every cell of the 13 lines
+//     through the old cell, +1 on those through the new one; the cell lists are rows of a
+//     neighbour table shared by all chains (geometry only, L2-resident), 32 cells per warp load.
+//   * cells are handled as linear ids c = (i*N+j)*N+k throughout; coordinates are only
+//     reconstructed when a state leaves the kernel.
+//   * per-chain shared memory is ~N^3 + 4*Q bytes (2.6 KB at N=12), so the register file, not
 //     shared memory, bounds residency.
 //
 // Table entries are uint8: T <= 13*N (12*N in board mode), so the kernel serves N <= 19 in
@@ -27,9 +31,14 @@
 
 namespace mcq {
 
+#ifndef MCQ_SPEC_MINB
+#define MCQ_SPEC_MINB 8   // min CTAs (of 4 warps) per SM the register allocation must allow
+#endif
+constexpr int MAX_NBR_ROUNDS = 8;   // 13*(N-1) <= 256 for every N the uint8 table admits
+
 // direction of the attack line of family f (same family order as make_coefs / line_ids);
 // the first non-zero component is always +1
-__device__ __forceinline__ void family_dir(int f, int &dx, int &dy, int &dz) {
+__host__ __device__ inline void family_dir(int f, int &dx, int &dy, int &dz) {
     // 2-bit fields (d+1), one base-4 digit per family, packed into immediates (no local array)
     // dx+1 per family F0..F12: 1,1,2,2,2,2,2,1,1,2,2,2,2
     // dy+1 per family F0..F12: 1,2,1,2,0,1,1,2,2,2,2,0,0
@@ -45,9 +54,9 @@ __device__ __forceinline__ void family_dir(int f, int &dx, int &dy, int &dz) {
     dz = (int)((PZ >> (2 * f)) & 3) - 1;
 }
 
-// Neighbour lists, shared by every chain of a launch (geometry only, L2-resident): row `cell` holds
-// the ids of all cells on the attack lines through `cell` (itself excluded), padded to a multiple
-// of 32 with the id N^3, a scratch byte at the end of every table, so updates need no predicate.
+// ---- geometry tables, built once per (mode, N) and shared by every chain ----------------------
+// nbr[cell][L]: ids of all cells on the attack lines through `cell` (itself excluded), padded to a
+// multiple of 32 with the id N^3, a scratch byte at the end of every T, so updates need no predicate.
 __global__ void build_neighbours_kernel(int full, int N, int L, uint16_t *nbr) {
     const int cell = blockIdx.x * blockDim.x + threadIdx.x;
     if (cell >= N * N * N) return;
@@ -67,7 +76,29 @@ __global__ void build_neighbours_kernel(int full, int N, int L, uint16_t *nbr) {
     for (; n < L; ++n) row[n] = (uint16_t)(N * N * N);
 }
 
-constexpr int MAX_NBR_ROUNDS = 8;   // 13*(N-1) <= 256 for every N the uint8 table admits
+// wide[c] = i*W^2 + j*W + k (W = 2N-1): the difference of two wide ids identifies (di,dj,dk);
+// lut bit (di+o)*W^2 + (dj+o)*W + (dk+o) (o = N-1) is set iff two cells that far apart share an
+// attack line: the non-zero |d| components are all equal (mcmc.py:149-167).
+__global__ void build_wide_lut_kernel(int N, uint16_t *wide, uint32_t *lut, int lut_words) {
+    const int W = 2 * N - 1, o = N - 1;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < N * N * N) {
+        const int x = idx / (N * N), y = (idx / N) % N, z = idx % N;
+        wide[idx] = (uint16_t)((x * W + y) * W + z);
+    }
+    if (idx < lut_words) {
+        uint32_t bits = 0u;
+        for (int b = 0; b < 32; ++b) {
+            const int e = idx * 32 + b;
+            if (e >= W * W * W) break;
+            const int da = abs(e / (W * W) - o), db = abs((e / W) % W - o), dc = abs(e % W - o);
+            const int m = max(da, max(db, dc));
+            const bool sh = m > 0 && (da == 0 || da == m) && (db == 0 || db == m) && (dc == 0 || dc == m);
+            bits |= (uint32_t)sh << b;
+        }
+        lut[idx] = bits;
+    }
+}
 
 // T[c] += delta for every cell c on the attack lines through one cell (its neighbour row).
 // All lanes must call; `nr` = row length / 32.
@@ -81,22 +112,43 @@ __device__ __forceinline__ void table_lines_add(uint8_t *T, const uint16_t *row,
         if (r < nr) T[c[r]] = (uint8_t)(T[c[r]] + delta);
 }
 
-template <bool FULL, bool REPLAY>
-__global__ void __launch_bounds__(128, 8) spec_kernel(const __grid_constant__ KArgs a) {
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// lane-0 scalars kept in the slab instead of registers
+enum RecSlot { R_NACC = 0, R_BEST_STEP, R_BIN_MARK, R_BIN, R_ACC_BLK, R_ACCBITS, R_NEAR, R_SLOTS };
+
+template <bool FULL, bool REPLAY, bool EARLY>
+__global__ void __launch_bounds__(128, MCQ_SPEC_MINB) spec_kernel(const __grid_constant__ KArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     constexpr unsigned FULLMASK = 0xffffffffu;
     constexpr int NF = FULL ? NFAM : NFAM - 1;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int chain = blockIdx.x * (blockDim.x >> 5) + wid;
-    const int N = a.N, rounds = a.sl.rounds;
+    const int lane = threadIdx.x & 31;
+    const int N = a.N;
+    const int N3 = N * N * N;
 
+    // ---- CTA-shared geometry: shared-line bits and cell -> wide id (full_3d only) ----
+    const uint32_t *lut = reinterpret_cast<const uint32_t *>(smem);
+    const uint16_t *wide = reinterpret_cast<const uint16_t *>(smem + a.sl.off_wide);
+    if (FULL) {
+        uint32_t *dst = reinterpret_cast<uint32_t *>(smem);
+        for (int w = threadIdx.x; w < a.sl.cta_bytes / 4; w += blockDim.x) dst[w] = __ldg(a.geo + w);
+        __syncthreads();
+    }
+    const int chain = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (chain >= a.n_chains) return;
-    const int L = a.sl.nbr_len;
 
-    unsigned char *S = smem + (size_t)wid * a.sl.stride;
+    unsigned char *S = smem + a.sl.cta_bytes + (size_t)(threadIdx.x >> 5) * a.sl.stride;
     uint8_t *T = S;
-    unsigned char *st = S + a.sl.off_state;
+    unsigned char *st = S + a.sl.off_state;                                  // board: heights
+    uint32_t *pos = reinterpret_cast<uint32_t *>(S + a.sl.off_state);        // full_3d: cell id | wide id << 16
     uint32_t *occ = reinterpret_cast<uint32_t *>(S + a.sl.off_occ);
+    int *rec = reinterpret_cast<int *>(S + a.sl.off_rec);
+    const int L = a.sl.nbr_len, rounds = a.sl.rounds;
+    const int wide_bias = (N - 1) * ((2 * N - 1) * (2 * N - 1) + (2 * N - 1) + 1);
 
     // ---- build the slab from the external state ----
     for (int w = lane; w < a.sl.stride / 4; w += 32) reinterpret_cast<uint32_t *>(S)[w] = 0u;
@@ -104,9 +156,8 @@ __global__ void __launch_bounds__(128, 8) spec_kernel(const __grid_constant__ KA
     const uint8_t *ext = a.state + (size_t)chain * a.state_bytes;
     for (int qi = lane; qi < a.Q; qi += 32) {
         if (FULL) {
-            const int i = ext[3 * qi], j = ext[3 * qi + 1], k = ext[3 * qi + 2];
-            store_pos(st, 0, qi, pack_pos(0, i, j, k));
-            const int cid = (i * N + j) * N + k;
+            const int cid = ((int)ext[3 * qi] * N + (int)ext[3 * qi + 1]) * N + (int)ext[3 * qi + 2];
+            pos[qi] = (uint32_t)cid | ((uint32_t)wide[cid] << 16);
             atomicOr(&occ[cid >> 5], 1u << (cid & 31));
         } else {
             st[qi] = ext[qi];
@@ -114,10 +165,7 @@ __global__ void __launch_bounds__(128, 8) spec_kernel(const __grid_constant__ KA
     }
     __syncwarp();
     for (int qi = 0; qi < a.Q; ++qi) {
-        int i, j, k;
-        if (FULL) unpack_pos(0, load_pos(st, 0, qi), i, j, k);
-        else { i = qi / N; j = qi - i * N; k = st[qi]; }
-        const int c = (i * N + j) * N + k;
+        const int c = FULL ? (int)(pos[qi] & 0xffffu) : qi * N + (int)st[qi];
         table_lines_add(T, a.nbr + (size_t)c * L, rounds, lane, 1);
         if (lane == 0) T[c] = (uint8_t)(T[c] + NF);
         __syncwarp();
@@ -126,18 +174,16 @@ __global__ void __launch_bounds__(128, 8) spec_kernel(const __grid_constant__ KA
     {
         int e = 0;
         for (int qi = lane; qi < a.Q; qi += 32) {
-            int i, j, k;
-            if (FULL) unpack_pos(0, load_pos(st, 0, qi), i, j, k);
-            else { i = qi / N; j = qi - i * N; k = st[qi]; }
-            e += (int)T[(i * N + j) * N + k] - NF;
+            const int c = FULL ? (int)(pos[qi] & 0xffffu) : qi * N + (int)st[qi];
+            e += (int)T[c] - NF;
         }
         E = __reduce_add_sync(FULLMASK, e) >> 1;   // every attacking pair was counted from both ends
     }
 
     // ---- persistent record ----
-    int best = E, best_step = 0, n_acc = 0, stale = 0, bin_mark = 0;
+    int best = E, stale = 0;
     int done = a.t_end;
-    bool active = true;
+    int t = a.t_begin;
     if (a.t_begin == 0) {
         if (lane == 0) {
             if (a.init_e) a.init_e[chain] = E;
@@ -146,13 +192,17 @@ __global__ void __launch_bounds__(128, 8) spec_kernel(const __grid_constant__ KA
         }
     } else {
         best = a.best_e[chain];
-        best_step = a.best_step[chain];
-        n_acc = a.n_acc[chain];
         stale = a.stale[chain];
-        bin_mark = a.bin_mark[chain];
+        if (lane == 0) {
+            rec[R_NACC] = a.n_acc[chain];
+            rec[R_BEST_STEP] = a.best_step[chain];
+            rec[R_BIN_MARK] = a.bin_mark[chain];
+        }
         const int sd = a.steps_done[chain];
-        if (sd < a.t_begin) { active = false; done = sd; }
+        if (sd < a.t_begin) { done = sd; t = a.t_end; }   // stopped in an earlier launch
     }
+    if (lane == 0) { rec[R_BIN] = a.bin_at_begin; rec[R_ACC_BLK] = a.t_begin >> 5; }
+    __syncwarp();
     const unsigned long long sd64 = a.seeds ? a.seeds[chain] : 0ull;
     const uint32_t key0 = (uint32_t)sd64, key1 = (uint32_t)(sd64 >> 32);
     const int grp = a.group ? a.group[chain] : 0;
@@ -160,124 +210,109 @@ __global__ void __launch_bounds__(128, 8) spec_kernel(const __grid_constant__ KA
     const double *beta64_row = REPLAY ? a.beta64 + (size_t)grp * a.n_steps : nullptr;
     const uint32_t *mv_row = REPLAY ? a.rmoves + (size_t)chain * a.n_steps : nullptr;
     const double *un_row = REPLAY ? a.runif + (size_t)chain * a.n_steps : nullptr;
+    int next_edge = a.n_bins > 0 ? a.bin_starts[a.bin_at_begin + 1] : 0x7fffffff;
+    // history row, addressed by history index h = step + 1 (h_origin = index held by column 0)
+    unsigned char *hrow = static_cast<unsigned char *>(a.hist) +
+                          ((long long)chain * a.hist_pitch - a.h_origin) * (a.hist_kind == 1 ? 2 : 4);
 
-    int bin = a.bin_at_begin;
-    int next_edge = a.n_bins > 0 ? a.bin_starts[bin + 1] : 0x7fffffff;
-    int acc_blk = a.t_begin >> 5;
-    uint32_t accbits = 0u, near = 0u;
-    uint16_t *hist16 = a.hist_kind == 1 ? reinterpret_cast<uint16_t *>(a.hist) + (size_t)chain * a.hist_pitch : nullptr;
-    int *hist32 = a.hist_kind == 2 ? reinterpret_cast<int *>(a.hist) + (size_t)chain * a.hist_pitch : nullptr;
-
-    int t = a.t_begin;
-    while (active && t < a.t_end) {
-        const int s = t + lane;
-        const bool valid = s < a.t_end;
-        const int n_valid = min(32, a.t_end - t);
+    while (t < a.t_end) {
+        const int rem = a.t_end - t;                       // >= 1
+        const bool valid = lane < rem;
+        const int s = t + (valid ? lane : rem - 1);        // lanes past the end redo the last step, masked below
 
         // ---------------- this lane's proposal: step s against the current state ----------------
-        int i0 = 0, j0 = 0, k0c = 0, i1 = 0, j1 = 0, k1c = 0, qsel = 0;
-        bool bad = false, accept = false;
-        uint32_t w_u = 0u;
-        float cb = 0.f;
-        double u64 = 0.0, b64 = 0.0;
-        if (valid) {
-            if constexpr (REPLAY) {
-                const uint32_t mv = mv_row[s];
-                u64 = un_row[s];
-                b64 = beta64_row[s];
-                if (FULL) {
-                    qsel = mv & 0xfff; i1 = (mv >> 12) & 63; j1 = (mv >> 18) & 63; k1c = (mv >> 24) & 63;
-                    bad = qsel >= a.Q || i1 >= N || j1 >= N || k1c >= N;
-                    if (bad) { qsel = 0; i1 = j1 = k1c = 0; }
-                    const int cid1 = (i1 * N + j1) * N + k1c;
-                    bad = bad || ((occ[cid1 >> 5] >> (cid1 & 31)) & 1u);
-                    unpack_pos(0, load_pos(st, 0, qsel), i0, j0, k0c);
-                } else {
-                    i0 = mv & 255; j0 = (mv >> 8) & 255; k1c = (mv >> 16) & 255;
-                    bad = i0 >= N || j0 >= N || k1c >= N;
-                    if (bad) { i0 = j0 = k1c = 0; }
-                    k0c = st[i0 * N + j0];
-                    bad = bad || (k1c == k0c);
-                    i1 = i0; j1 = j0;
-                }
-            } else {
-                cb = __ldg(beta_row + s);
-                const Philox4 r = philox4x32_10((uint32_t)s, 0u, 0u, PHILOX_DOMAIN_STEP, key0, key1);
-                w_u = r.z;
-                if (FULL) {
-                    qsel = (int)__umulhi(r.x, (uint32_t)a.Q);
-                    uint32_t word = r.y;
-                    int tries = 0;
-                    while (true) {
-                        i1 = draw_digit(word, N); j1 = draw_digit(word, N); k1c = draw_digit(word, N);
-                        const int cid1 = (i1 * N + j1) * N + k1c;
-                        if (!((occ[cid1 >> 5] >> (cid1 & 31)) & 1u)) break;
-                        if (tries == 0) word = r.w;
-                        else {
-                            const int e = tries - 1;
-                            const Philox4 r2 = philox4x32_10((uint32_t)s, 0u, 1u + (uint32_t)(e >> 2), PHILOX_DOMAIN_STEP, key0, key1);
-                            const int sel = e & 3;
-                            word = sel == 0 ? r2.x : sel == 1 ? r2.y : sel == 2 ? r2.z : r2.w;
-                        }
-                        ++tries;
-                    }
-                    unpack_pos(0, load_pos(st, 0, qsel), i0, j0, k0c);
-                } else {
-                    uint32_t word = r.x;
-                    i0 = draw_digit(word, N); j0 = draw_digit(word, N);
-                    k0c = st[i0 * N + j0];
-                    k1c = k0c + 1 + (int)__umulhi(r.y, (uint32_t)(N - 1));
-                    k1c -= (k1c >= N) ? N : 0;
-                    i1 = i0; j1 = j0;
-                }
-            }
-        }
-        // ---------------- delta-E: two table reads ----------------
+        uint32_t c0, c1, aux;   // old cell, new cell, and what the commit needs besides them
         int dE;
-        {
-            const int c0 = (i0 * N + j0) * N + k0c, c1 = (i1 * N + j1) * N + k1c;
-            dE = (int)T[c1] - (int)T[c0] + NF;
-            if (FULL) {
-                const int da = abs(i1 - i0), db = abs(j1 - j0), dc = abs(k1c - k0c);
-                const int m = max(da, max(db, dc));
-                const bool shared = (da == 0 || da == m) && (db == 0 || db == m) && (dc == 0 || dc == m);
-                dE -= shared ? 1 : 0;   // the moving queen itself sits on a line through the new cell
-            }
-        }
-        // ---------------- Metropolis test ----------------
-        bool near_flag = false;
+        bool accept;
+        [[maybe_unused]] bool bad = false, near_flag = false;
         if constexpr (REPLAY) {
+            const uint32_t mv = mv_row[s];
+            const double u64 = un_row[s], b64 = beta64_row[s];
+            if (FULL) {
+                uint32_t q = mv & 0xfff;
+                const uint32_t i1 = (mv >> 12) & 63, j1 = (mv >> 18) & 63, k1 = (mv >> 24) & 63;
+                bad = q >= (uint32_t)a.Q || i1 >= (uint32_t)N || j1 >= (uint32_t)N || k1 >= (uint32_t)N;
+                c1 = bad ? 0u : (i1 * N + j1) * N + k1;
+                if (bad) q = 0;
+                bad = bad || ((occ[c1 >> 5] >> (c1 & 31)) & 1u);
+                const uint32_t p0 = pos[q], w1 = wide[c1];
+                c0 = p0 & 0xffffu;
+                const uint32_t e = w1 - (p0 >> 16) + (uint32_t)wide_bias;
+                dE = (int)T[c1] - (int)T[c0] + NF - (int)((lut[e >> 5] >> (e & 31)) & 1u);
+                aux = q | (w1 << 16);
+            } else {
+                uint32_t i0 = mv & 255, j0 = (mv >> 8) & 255, k1 = (mv >> 16) & 255;
+                bad = i0 >= (uint32_t)N || j0 >= (uint32_t)N || k1 >= (uint32_t)N;
+                if (bad) { i0 = j0 = k1 = 0; }
+                const uint32_t ij = i0 * N + j0, k0 = st[ij];
+                bad = bad || (k1 == k0);
+                c0 = ij * N + k0; c1 = ij * N + k1;
+                dE = (int)T[c1] - (int)T[c0] + NF;
+                aux = ij | (k1 << 16);
+            }
             const double p = exp(-b64 * (double)dE);
-            accept = u64 < fmin(1.0, p);
-            near_flag = valid && !bad && fabs(u64 - p) < 1e-6;
-            if (bad) accept = false;
+            accept = !bad && u64 < fmin(1.0, p);
+            near_flag = !bad && fabs(u64 - p) < 1e-6;
         } else {
-            const float p = exp2f(cb * (float)dE);
-            const uint32_t thr = __float2uint_rz(p * 4294967296.0f);
-            accept = (dE <= 0) || (w_u < thr);
+            const float cb = __ldg(beta_row + s);
+            const Philox4 r = philox4x32_10((uint32_t)s, 0u, 0u, PHILOX_DOMAIN_STEP, key0, key1);
+            if (FULL) {
+                const uint32_t q = __umulhi(r.x, (uint32_t)a.Q);
+                const uint32_t p0 = pos[q];
+                // uniform over the empty cells: redraw while occupied (the queen's own cell counts,
+                // experiments.py:226-231).  mulhi(word, N^3) == the (i,j,k) digits of anneal_kernel.
+                uint32_t word = r.y;
+                int tries = 0;
+                while (true) {
+                    c1 = __umulhi(word, (uint32_t)N3);
+                    if (!((occ[c1 >> 5] >> (c1 & 31)) & 1u)) break;
+                    if (tries == 0) word = r.w;
+                    else {
+                        const int e = tries - 1;
+                        const Philox4 r2 = philox4x32_10((uint32_t)s, 0u, 1u + (uint32_t)(e >> 2), PHILOX_DOMAIN_STEP, key0, key1);
+                        const int sel = e & 3;
+                        word = sel == 0 ? r2.x : sel == 1 ? r2.y : sel == 2 ? r2.z : r2.w;
+                    }
+                    ++tries;
+                }
+                const uint32_t w1 = wide[c1];
+                c0 = p0 & 0xffffu;
+                const uint32_t e = w1 - (p0 >> 16) + (uint32_t)wide_bias;
+                // the moving queen itself sits on a line through the new cell iff the cells share one
+                dE = (int)T[c1] - (int)T[c0] + NF - (int)((lut[e >> 5] >> (e & 31)) & 1u);
+                aux = q | (w1 << 16);
+            } else {
+                const uint32_t ij = __umulhi(r.x, (uint32_t)(N * N));
+                const uint32_t k0 = st[ij];
+                // uniform over the N-1 other heights (== the redraw loop of experiments.py:317-319)
+                uint32_t k1 = k0 + 1u + __umulhi(r.y, (uint32_t)(N - 1));
+                k1 -= (k1 >= (uint32_t)N) ? (uint32_t)N : 0u;
+                c0 = ij * N + k0; c1 = ij * N + k1;
+                dE = (int)T[c1] - (int)T[c0] + NF;
+                aux = ij | (k1 << 16);
+            }
+            // Metropolis (experiments.py:238-239 / :326-327): u < exp(-beta dE), u = (word + 0.5) / 2^32
+            const float p = ex2_approx(cb * (float)dE);
+            const uint32_t thr = __float2uint_rz(p * 4294967296.0f);   // saturates at 2^32 - 1
+            accept = (dE <= 0) || (r.z < thr);
         }
         accept = accept && valid;
 
         // ---------------- commit the first accepted proposal ----------------
         const unsigned acc_mask = __ballot_sync(FULLMASK, accept);
         int first = acc_mask ? __ffs(acc_mask) - 1 : -1;
-        int adv = first >= 0 ? first + 1 : n_valid;   // steps consumed by this round
-        int adv_h = adv;                              // steps whose energy is appended to the history
+        int adv = first >= 0 ? first + 1 : min(32, rem);   // steps consumed by this round
+        int adv_h = adv;                                   // steps whose energy is appended to the history
         bool stop = false;
         int E_new = E;
-        bool improved = false;
-        int w_dE = 0;
-        if (first >= 0) {
-            w_dE = __shfl_sync(FULLMASK, dE, first);
-            E_new = E + w_dE;
-            improved = E_new < best;
-        }
-        if (!FULL && a.patience >= 0) {
+        if (first >= 0) E_new = E + __shfl_sync(FULLMASK, dE, first);
+        bool improved = E_new < best;
+        if constexpr (EARLY) {
             // experiments.py:343-353: the counter resets on a strict improvement only, and the
             // break happens before the history append of the stopping step
             const int e_stop = max(a.patience - stale - 1, 0);   // rejected step at which patience runs out
             if (first < 0 || first > e_stop) {
-                if (e_stop < n_valid) { stop = true; first = -1; adv = e_stop + 1; adv_h = e_stop; stale += e_stop + 1; E_new = E; improved = false; }
+                if (e_stop < min(32, rem)) { stop = true; first = -1; adv = e_stop + 1; adv_h = e_stop; stale += e_stop + 1; E_new = E; improved = false; }
                 else stale += adv;
             } else {
                 stale = improved ? 0 : stale + first + 1;
@@ -286,65 +321,72 @@ __global__ void __launch_bounds__(128, 8) spec_kernel(const __grid_constant__ KA
         }
         if constexpr (REPLAY) {
             const unsigned committed = adv >= 32 ? FULLMASK : ((1u << adv) - 1u);
-            near += __popc(__ballot_sync(FULLMASK, near_flag) & committed);
+            const unsigned nearm = __ballot_sync(FULLMASK, near_flag && valid) & committed;
             const unsigned badm = __ballot_sync(FULLMASK, bad && valid) & committed;
-            if (badm && lane == 0) atomicAdd(a.replay_err, (unsigned)__popc(badm));
+            if (lane == 0) {
+                rec[R_NEAR] += __popc(nearm);
+                if (badm) atomicAdd(a.replay_err, (unsigned)__popc(badm));
+            }
         }
         // history: steps t .. t+adv_h-1; all but an accepted last one keep the old energy
-        if (lane < adv_h) {
+        if (lane < adv_h && a.hist_kind) {
             const int v = (lane == first) ? E_new : E;
-            const long long h = (long long)s + 1 - a.h_origin;
-            if (hist16) hist16[h] = (uint16_t)v;
-            else if (hist32) hist32[h] = v;
+            if (a.hist_kind == 1) reinterpret_cast<uint16_t *>(hrow)[s + 1] = (uint16_t)v;
+            else reinterpret_cast<int *>(hrow)[s + 1] = v;
         }
         // acceptance bins: close every bin that ends at or before the last consumed step
-        const int t_last = t + adv - 1;
-        while (t_last >= next_edge) {
-            if (lane == 0 && a.acc_hist) a.acc_hist[(size_t)chain * a.n_bins + bin] = (uint32_t)(n_acc - bin_mark);
-            bin_mark = n_acc;
-            ++bin;
-            next_edge = a.bin_starts[bin + 1];
+        if (t + adv - 1 >= next_edge) {
+            int bin = rec[R_BIN];
+            const int n_acc = rec[R_NACC];
+            while (t + adv - 1 >= next_edge) {
+                if (lane == 0) {
+                    if (a.acc_hist) a.acc_hist[(size_t)chain * a.n_bins + bin] = (uint32_t)(n_acc - rec[R_BIN_MARK]);
+                    rec[R_BIN_MARK] = n_acc;
+                }
+                ++bin;
+                next_edge = a.bin_starts[bin + 1];
+            }
+            if (lane == 0) rec[R_BIN] = bin;
+            __syncwarp();
         }
         if (first >= 0) {
-            const int wq = __shfl_sync(FULLMASK, qsel, first);
-            const int wc0 = __shfl_sync(FULLMASK, i0 | (j0 << 8) | (k0c << 16), first);
-            const int wc1 = __shfl_sync(FULLMASK, i1 | (j1 << 8) | (k1c << 16), first);
-            const int ai = wc0 & 255, aj = (wc0 >> 8) & 255, ak = wc0 >> 16;
-            const int bi = wc1 & 255, bj = (wc1 >> 8) & 255, bk = wc1 >> 16;
-            const int ca = (ai * N + aj) * N + ak, cbn = (bi * N + bj) * N + bk;
-            table_lines_add(T, a.nbr + (size_t)ca * L, rounds, lane, -1);
-            if (lane == 0) T[ca] = (uint8_t)(T[ca] - NF);
+            const uint32_t wc0 = __shfl_sync(FULLMASK, c0, first);
+            const uint32_t wc1 = __shfl_sync(FULLMASK, c1, first);
+            const uint32_t waux = __shfl_sync(FULLMASK, aux, first);
+            table_lines_add(T, a.nbr + (size_t)wc0 * L, rounds, lane, -1);
+            if (lane == 0) T[wc0] = (uint8_t)(T[wc0] - NF);
             __syncwarp();
-            table_lines_add(T, a.nbr + (size_t)cbn * L, rounds, lane, +1);
+            table_lines_add(T, a.nbr + (size_t)wc1 * L, rounds, lane, +1);
             if (lane == 0) {
-                T[cbn] = (uint8_t)(T[cbn] + NF);
+                T[wc1] = (uint8_t)(T[wc1] + NF);
                 if (FULL) {
-                    occ[ca >> 5] &= ~(1u << (ca & 31));
-                    occ[cbn >> 5] |= 1u << (cbn & 31);
-                    store_pos(st, 0, wq, pack_pos(0, bi, bj, bk));
+                    occ[wc0 >> 5] &= ~(1u << (wc0 & 31));
+                    occ[wc1 >> 5] |= 1u << (wc1 & 31);
+                    pos[waux & 0xffffu] = wc1 | (waux & 0xffff0000u);
                 } else {
-                    st[ai * N + aj] = (unsigned char)bk;
+                    st[waux & 0xffffu] = (unsigned char)(waux >> 16);
                 }
+                // accept bookkeeping lives with lane 0
+                const int ta = t + first;
+                rec[R_NACC] += 1;
+                if ((ta >> 5) != rec[R_ACC_BLK]) {
+                    if (rec[R_ACCBITS] && a.abits) a.abits[(size_t)chain * a.abits_pitch + rec[R_ACC_BLK]] = (uint32_t)rec[R_ACCBITS];
+                    rec[R_ACC_BLK] = ta >> 5;
+                    rec[R_ACCBITS] = 0;
+                }
+                rec[R_ACCBITS] |= (int)(1u << (ta & 31));
+                if (improved && !stop) rec[R_BEST_STEP] = ta + 1;
             }
             __syncwarp();
             E = E_new;
-            ++n_acc;
-            const int ta = t + first;
-            if ((ta >> 5) != acc_blk) {
-                if (accbits && lane == 0 && a.abits) a.abits[(size_t)chain * a.abits_pitch + acc_blk] = accbits;
-                acc_blk = ta >> 5;
-                accbits = 0u;
-            }
-            accbits |= 1u << (ta & 31);
             if (improved) {
+                // snapshot: the state at the first visit of the minimum (strict <, :252 / :340)
                 best = E;
-                if (!stop) best_step = ta + 1;
                 uint8_t *bs = a.best_state + (size_t)chain * a.state_bytes;
                 if (FULL) {
                     for (int qi = lane; qi < a.Q; qi += 32) {
-                        int i, j, k;
-                        unpack_pos(0, load_pos(st, 0, qi), i, j, k);
-                        bs[3 * qi] = (uint8_t)i; bs[3 * qi + 1] = (uint8_t)j; bs[3 * qi + 2] = (uint8_t)k;
+                        const int c = (int)(pos[qi] & 0xffffu);
+                        bs[3 * qi] = (uint8_t)(c / (N * N)); bs[3 * qi + 1] = (uint8_t)((c / N) % N); bs[3 * qi + 2] = (uint8_t)(c % N);
                     }
                 } else {
                     for (int c = lane; c < a.Q; c += 32) bs[c] = st[c];
@@ -352,36 +394,36 @@ __global__ void __launch_bounds__(128, 8) spec_kernel(const __grid_constant__ KA
             }
         }
         if (stop) {
-            active = false;
             done = t + adv - 1;
-            if (lane == 0 && a.acc_hist) a.acc_hist[(size_t)chain * a.n_bins + bin] = (uint32_t)(n_acc - bin_mark);
+            if (lane == 0 && a.acc_hist) a.acc_hist[(size_t)chain * a.n_bins + rec[R_BIN]] = (uint32_t)(rec[R_NACC] - rec[R_BIN_MARK]);
+            break;
         }
         t += adv;
     }
 
     // ---------------- write the record back ----------------
-    if (accbits && lane == 0 && a.abits) a.abits[(size_t)chain * a.abits_pitch + acc_blk] = accbits;
-    if (a.t_end == a.n_steps && a.n_bins > 0 && lane == 0 && a.acc_hist && done == a.t_end)
-        a.acc_hist[(size_t)chain * a.n_bins + bin] = (uint32_t)(n_acc - bin_mark);
+    __syncwarp();
+    if (lane == 0) {
+        if (rec[R_ACCBITS] && a.abits) a.abits[(size_t)chain * a.abits_pitch + rec[R_ACC_BLK]] = (uint32_t)rec[R_ACCBITS];
+        if (a.t_end == a.n_steps && a.n_bins > 0 && a.acc_hist && done == a.t_end)
+            a.acc_hist[(size_t)chain * a.n_bins + rec[R_BIN]] = (uint32_t)(rec[R_NACC] - rec[R_BIN_MARK]);
+        a.cur_e[chain] = E;
+        a.best_e[chain] = best;
+        a.best_step[chain] = rec[R_BEST_STEP];
+        a.n_acc[chain] = rec[R_NACC];
+        a.stale[chain] = stale;
+        a.bin_mark[chain] = rec[R_BIN_MARK];
+        a.steps_done[chain] = done;
+        if (REPLAY && a.near_cnt) a.near_cnt[chain] += (uint32_t)rec[R_NEAR];
+    }
     uint8_t *out = a.state + (size_t)chain * a.state_bytes;
     if (FULL) {
         for (int qi = lane; qi < a.Q; qi += 32) {
-            int i, j, k;
-            unpack_pos(0, load_pos(st, 0, qi), i, j, k);
-            out[3 * qi] = (uint8_t)i; out[3 * qi + 1] = (uint8_t)j; out[3 * qi + 2] = (uint8_t)k;
+            const int c = (int)(pos[qi] & 0xffffu);
+            out[3 * qi] = (uint8_t)(c / (N * N)); out[3 * qi + 1] = (uint8_t)((c / N) % N); out[3 * qi + 2] = (uint8_t)(c % N);
         }
     } else {
         for (int c = lane; c < a.Q; c += 32) out[c] = st[c];
-    }
-    if (lane == 0) {
-        a.cur_e[chain] = E;
-        a.best_e[chain] = best;
-        a.best_step[chain] = best_step;
-        a.n_acc[chain] = n_acc;
-        a.stale[chain] = stale;
-        a.bin_mark[chain] = bin_mark;
-        a.steps_done[chain] = done;
-        if (REPLAY && a.near_cnt) a.near_cnt[chain] += near;
     }
 }
 

@@ -51,6 +51,9 @@ if which == "base":
         for n in (8, 15, 20):
             run("N", mode, n, 8192, 10000)
     run("N", "board", 64, 1184, 2000)
+elif which == "quick":
+    run("q", "full_3d", 12, 20480, 200000, algo="table")
+    run("q", "board", 12, 20480, 100000, algo="table")
 elif which == "table":
     for mode in ("full_3d", "board"):
         for w in (1, 2, 4):
