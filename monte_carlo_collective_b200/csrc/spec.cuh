@@ -100,16 +100,35 @@ __global__ void build_wide_lut_kernel(int N, uint16_t *wide, uint32_t *lut, int 
     }
 }
 
-// T[c] += delta for every cell c on the attack lines through one cell (its neighbour row).
-// All lanes must call; `nr` = row length / 32.
-__device__ __forceinline__ void table_lines_add(uint8_t *T, const uint16_t *row, int nr, int lane, int delta) {
-    int c[MAX_NBR_ROUNDS];
+// ---- shared memory is addressed by 32-bit byte offsets into the dynamic array -----------------
+// (no generic pointers: one base register per slab instead of 64-bit pointer pairs)
+extern __shared__ __align__(16) unsigned char smem[];
+#define SM8(off) (smem[(off)])
+#define SM16(off) (*reinterpret_cast<uint16_t *>(smem + (off)))
+#define SM32(off) (*reinterpret_cast<uint32_t *>(smem + (off)))
+
+// T[c] += delta for every cell c on the attack lines through one cell (its neighbour row of NR*32
+// ids).  sT = byte offset of the chain's table.  All lanes must call.
+template <int NR>
+__device__ __forceinline__ void table_row_add(int sT, const uint16_t *row, int lane, int delta) {
+    int c[NR];
 #pragma unroll
-    for (int r = 0; r < MAX_NBR_ROUNDS; ++r)
-        if (r < nr) c[r] = __ldg(row + r * 32 + lane);
+    for (int r = 0; r < NR; ++r) c[r] = __ldg(row + r * 32 + lane);
 #pragma unroll
-    for (int r = 0; r < MAX_NBR_ROUNDS; ++r)
-        if (r < nr) T[c[r]] = (uint8_t)(T[c[r]] + delta);
+    for (int r = 0; r < NR; ++r) SM8(sT + c[r]) = (unsigned char)(SM8(sT + c[r]) + delta);
+}
+
+__device__ __forceinline__ void table_lines_add(int sT, const uint16_t *row, int nr, int lane, int delta) {
+    switch (nr) {
+        case 1: table_row_add<1>(sT, row, lane, delta); break;
+        case 2: table_row_add<2>(sT, row, lane, delta); break;
+        case 3: table_row_add<3>(sT, row, lane, delta); break;
+        case 4: table_row_add<4>(sT, row, lane, delta); break;
+        case 5: table_row_add<5>(sT, row, lane, delta); break;
+        case 6: table_row_add<6>(sT, row, lane, delta); break;
+        case 7: table_row_add<7>(sT, row, lane, delta); break;
+        default: table_row_add<8>(sT, row, lane, delta); break;
+    }
 }
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -118,70 +137,64 @@ __device__ __forceinline__ float ex2_approx(float x) {
     return y;
 }
 
-// lane-0 scalars kept in the slab instead of registers
-enum RecSlot { R_NACC = 0, R_BEST_STEP, R_BIN_MARK, R_BIN, R_ACC_BLK, R_ACCBITS, R_NEAR, R_SLOTS };
+// lane-0 scalars kept in the slab instead of registers (byte offsets from sl.off_rec)
+enum RecSlot { R_BEST_STEP = 0, R_BIN_MARK = 4, R_BIN = 8, R_NEAR = 12 };
 
 template <bool FULL, bool REPLAY, bool EARLY>
 __global__ void __launch_bounds__(128, MCQ_SPEC_MINB) spec_kernel(const __grid_constant__ KArgs a) {
-    extern __shared__ __align__(16) unsigned char smem[];
     constexpr unsigned FULLMASK = 0xffffffffu;
     constexpr int NF = FULL ? NFAM : NFAM - 1;
     const int lane = threadIdx.x & 31;
     const int N = a.N;
-    const int N3 = N * N * N;
 
-    // ---- CTA-shared geometry: shared-line bits and cell -> wide id (full_3d only) ----
-    const uint32_t *lut = reinterpret_cast<const uint32_t *>(smem);
-    const uint16_t *wide = reinterpret_cast<const uint16_t *>(smem + a.sl.off_wide);
+    // ---- CTA-shared geometry: shared-line bits at offset 0, cell -> wide id at sl.off_wide ----
     if (FULL) {
-        uint32_t *dst = reinterpret_cast<uint32_t *>(smem);
-        for (int w = threadIdx.x; w < a.sl.cta_bytes / 4; w += blockDim.x) dst[w] = __ldg(a.geo + w);
+        for (int w = threadIdx.x; w < a.sl.cta_bytes / 4; w += blockDim.x) SM32(4 * w) = __ldg(a.geo + w);
         __syncthreads();
     }
     const int chain = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (chain >= a.n_chains) return;
 
-    unsigned char *S = smem + a.sl.cta_bytes + (size_t)(threadIdx.x >> 5) * a.sl.stride;
-    uint8_t *T = S;
-    unsigned char *st = S + a.sl.off_state;                                  // board: heights
-    uint32_t *pos = reinterpret_cast<uint32_t *>(S + a.sl.off_state);        // full_3d: cell id | wide id << 16
-    uint32_t *occ = reinterpret_cast<uint32_t *>(S + a.sl.off_occ);
-    int *rec = reinterpret_cast<int *>(S + a.sl.off_rec);
+    const int sT = a.sl.cta_bytes + (int)(threadIdx.x >> 5) * a.sl.stride;   // table T[N^3 + 1]
+    const int sP = sT + a.sl.off_state;   // board: heights u8; full_3d: u32 per queen = cell id | wide id << 16
+    const int sO = sT + a.sl.off_occ;     // full_3d: occupancy bits
+    const int sR = sT + a.sl.off_rec;     // lane-0 record
+    const int sW = a.sl.off_wide;
     const int L = a.sl.nbr_len, rounds = a.sl.rounds;
-    const int wide_bias = (N - 1) * ((2 * N - 1) * (2 * N - 1) + (2 * N - 1) + 1);
+    const uint32_t wide_bias = (uint32_t)((N - 1) * ((2 * N - 1) * (2 * N - 1) + (2 * N - 1) + 1));
 
     // ---- build the slab from the external state ----
-    for (int w = lane; w < a.sl.stride / 4; w += 32) reinterpret_cast<uint32_t *>(S)[w] = 0u;
+    for (int w = lane; w < a.sl.stride / 4; w += 32) SM32(sT + 4 * w) = 0u;
     __syncwarp();
     const uint8_t *ext = a.state + (size_t)chain * a.state_bytes;
     for (int qi = lane; qi < a.Q; qi += 32) {
         if (FULL) {
             const int cid = ((int)ext[3 * qi] * N + (int)ext[3 * qi + 1]) * N + (int)ext[3 * qi + 2];
-            pos[qi] = (uint32_t)cid | ((uint32_t)wide[cid] << 16);
-            atomicOr(&occ[cid >> 5], 1u << (cid & 31));
+            SM32(sP + 4 * qi) = (uint32_t)cid | ((uint32_t)SM16(sW + 2 * cid) << 16);
+            atomicOr(&SM32(sO + 4 * (cid >> 5)), 1u << (cid & 31));
         } else {
-            st[qi] = ext[qi];
+            SM8(sP + qi) = ext[qi];
         }
     }
     __syncwarp();
     for (int qi = 0; qi < a.Q; ++qi) {
-        const int c = FULL ? (int)(pos[qi] & 0xffffu) : qi * N + (int)st[qi];
-        table_lines_add(T, a.nbr + (size_t)c * L, rounds, lane, 1);
-        if (lane == 0) T[c] = (uint8_t)(T[c] + NF);
+        const int c = FULL ? (int)(SM32(sP + 4 * qi) & 0xffffu) : qi * N + (int)SM8(sP + qi);
+        table_lines_add(sT, a.nbr + (size_t)c * L, rounds, lane, 1);
+        if (lane == 0) SM8(sT + c) = (unsigned char)(SM8(sT + c) + NF);
         __syncwarp();
     }
     int E;
     {
         int e = 0;
         for (int qi = lane; qi < a.Q; qi += 32) {
-            const int c = FULL ? (int)(pos[qi] & 0xffffu) : qi * N + (int)st[qi];
-            e += (int)T[c] - NF;
+            const int c = FULL ? (int)(SM32(sP + 4 * qi) & 0xffffu) : qi * N + (int)SM8(sP + qi);
+            e += (int)SM8(sT + c) - NF;
         }
         E = __reduce_add_sync(FULLMASK, e) >> 1;   // every attacking pair was counted from both ends
     }
 
     // ---- persistent record ----
-    int best = E, stale = 0;
+    int best = E, stale = 0, n_acc = 0;
     int done = a.t_end;
     int t = a.t_begin;
     if (a.t_begin == 0) {
@@ -193,15 +206,15 @@ __global__ void __launch_bounds__(128, MCQ_SPEC_MINB) spec_kernel(const __grid_c
     } else {
         best = a.best_e[chain];
         stale = a.stale[chain];
+        n_acc = a.n_acc[chain];
         if (lane == 0) {
-            rec[R_NACC] = a.n_acc[chain];
-            rec[R_BEST_STEP] = a.best_step[chain];
-            rec[R_BIN_MARK] = a.bin_mark[chain];
+            SM32(sR + R_BEST_STEP) = (uint32_t)a.best_step[chain];
+            SM32(sR + R_BIN_MARK) = (uint32_t)a.bin_mark[chain];
         }
         const int sd = a.steps_done[chain];
         if (sd < a.t_begin) { done = sd; t = a.t_end; }   // stopped in an earlier launch
     }
-    if (lane == 0) { rec[R_BIN] = a.bin_at_begin; rec[R_ACC_BLK] = a.t_begin >> 5; }
+    if (lane == 0) SM32(sR + R_BIN) = (uint32_t)a.bin_at_begin;
     __syncwarp();
     const unsigned long long sd64 = a.seeds ? a.seeds[chain] : 0ull;
     const uint32_t key0 = (uint32_t)sd64, key1 = (uint32_t)(sd64 >> 32);
@@ -214,6 +227,7 @@ __global__ void __launch_bounds__(128, MCQ_SPEC_MINB) spec_kernel(const __grid_c
     // history row, addressed by history index h = step + 1 (h_origin = index held by column 0)
     unsigned char *hrow = static_cast<unsigned char *>(a.hist) +
                           ((long long)chain * a.hist_pitch - a.h_origin) * (a.hist_kind == 1 ? 2 : 4);
+    uint32_t *abits_row = a.abits ? a.abits + (size_t)chain * a.abits_pitch : nullptr;
 
     while (t < a.t_end) {
         const int rem = a.t_end - t;                       // >= 1
@@ -234,20 +248,20 @@ __global__ void __launch_bounds__(128, MCQ_SPEC_MINB) spec_kernel(const __grid_c
                 bad = q >= (uint32_t)a.Q || i1 >= (uint32_t)N || j1 >= (uint32_t)N || k1 >= (uint32_t)N;
                 c1 = bad ? 0u : (i1 * N + j1) * N + k1;
                 if (bad) q = 0;
-                bad = bad || ((occ[c1 >> 5] >> (c1 & 31)) & 1u);
-                const uint32_t p0 = pos[q], w1 = wide[c1];
+                bad = bad || ((SM32(sO + 4 * (c1 >> 5)) >> (c1 & 31)) & 1u);
+                const uint32_t p0 = SM32(sP + 4 * q), w1 = SM16(sW + 2 * c1);
                 c0 = p0 & 0xffffu;
-                const uint32_t e = w1 - (p0 >> 16) + (uint32_t)wide_bias;
-                dE = (int)T[c1] - (int)T[c0] + NF - (int)((lut[e >> 5] >> (e & 31)) & 1u);
+                const uint32_t e = w1 - (p0 >> 16) + wide_bias;
+                dE = (int)SM8(sT + c1) - (int)SM8(sT + c0) + NF - (int)((SM32(4 * (e >> 5)) >> (e & 31)) & 1u);
                 aux = q | (w1 << 16);
             } else {
                 uint32_t i0 = mv & 255, j0 = (mv >> 8) & 255, k1 = (mv >> 16) & 255;
                 bad = i0 >= (uint32_t)N || j0 >= (uint32_t)N || k1 >= (uint32_t)N;
                 if (bad) { i0 = j0 = k1 = 0; }
-                const uint32_t ij = i0 * N + j0, k0 = st[ij];
+                const uint32_t ij = i0 * N + j0, k0 = SM8(sP + ij);
                 bad = bad || (k1 == k0);
                 c0 = ij * N + k0; c1 = ij * N + k1;
-                dE = (int)T[c1] - (int)T[c0] + NF;
+                dE = (int)SM8(sT + c1) - (int)SM8(sT + c0) + NF;
                 aux = ij | (k1 << 16);
             }
             const double p = exp(-b64 * (double)dE);
@@ -257,41 +271,41 @@ __global__ void __launch_bounds__(128, MCQ_SPEC_MINB) spec_kernel(const __grid_c
             const float cb = __ldg(beta_row + s);
             const Philox4 r = philox4x32_10((uint32_t)s, 0u, 0u, PHILOX_DOMAIN_STEP, key0, key1);
             if (FULL) {
+                const uint32_t N3 = (uint32_t)(N * N * N);
                 const uint32_t q = __umulhi(r.x, (uint32_t)a.Q);
-                const uint32_t p0 = pos[q];
+                const uint32_t p0 = SM32(sP + 4 * q);
                 // uniform over the empty cells: redraw while occupied (the queen's own cell counts,
                 // experiments.py:226-231).  mulhi(word, N^3) == the (i,j,k) digits of anneal_kernel.
-                uint32_t word = r.y;
-                int tries = 0;
-                while (true) {
-                    c1 = __umulhi(word, (uint32_t)N3);
-                    if (!((occ[c1 >> 5] >> (c1 & 31)) & 1u)) break;
-                    if (tries == 0) word = r.w;
-                    else {
-                        const int e = tries - 1;
+                // The first two candidates (words y, w) are resolved without a branch.
+                c1 = __umulhi(r.y, N3);
+                const uint32_t c1b = __umulhi(r.w, N3);
+                if ((SM32(sO + 4 * (c1 >> 5)) >> (c1 & 31)) & 1u) {
+                    c1 = c1b;
+                    int e = 0;
+                    while ((SM32(sO + 4 * (c1 >> 5)) >> (c1 & 31)) & 1u) {
                         const Philox4 r2 = philox4x32_10((uint32_t)s, 0u, 1u + (uint32_t)(e >> 2), PHILOX_DOMAIN_STEP, key0, key1);
                         const int sel = e & 3;
-                        word = sel == 0 ? r2.x : sel == 1 ? r2.y : sel == 2 ? r2.z : r2.w;
+                        c1 = __umulhi(sel == 0 ? r2.x : sel == 1 ? r2.y : sel == 2 ? r2.z : r2.w, N3);
+                        ++e;
                     }
-                    ++tries;
                 }
-                const uint32_t w1 = wide[c1];
+                const uint32_t w1 = SM16(sW + 2 * c1);
                 c0 = p0 & 0xffffu;
-                const uint32_t e = w1 - (p0 >> 16) + (uint32_t)wide_bias;
+                const uint32_t e = w1 - (p0 >> 16) + wide_bias;
                 // the moving queen itself sits on a line through the new cell iff the cells share one
-                dE = (int)T[c1] - (int)T[c0] + NF - (int)((lut[e >> 5] >> (e & 31)) & 1u);
+                dE = (int)SM8(sT + c1) - (int)SM8(sT + c0) + NF - (int)((SM32(4 * (e >> 5)) >> (e & 31)) & 1u);
                 aux = q | (w1 << 16);
             } else {
                 const uint32_t ij = __umulhi(r.x, (uint32_t)(N * N));
-                const uint32_t k0 = st[ij];
+                const uint32_t k0 = SM8(sP + ij);
                 // uniform over the N-1 other heights (== the redraw loop of experiments.py:317-319)
                 uint32_t k1 = k0 + 1u + __umulhi(r.y, (uint32_t)(N - 1));
                 k1 -= (k1 >= (uint32_t)N) ? (uint32_t)N : 0u;
                 c0 = ij * N + k0; c1 = ij * N + k1;
-                dE = (int)T[c1] - (int)T[c0] + NF;
+                dE = (int)SM8(sT + c1) - (int)SM8(sT + c0) + NF;
                 aux = ij | (k1 << 16);
             }
-            // Metropolis (experiments.py:238-239 / :326-327): u < exp(-beta dE), u = (word + 0.5) / 2^32
+            // Metropolis (experiments.py:238-239 / :326-327): u < exp(-beta dE), u = word / 2^32
             const float p = ex2_approx(cb * (float)dE);
             const uint32_t thr = __float2uint_rz(p * 4294967296.0f);   // saturates at 2^32 - 1
             accept = (dE <= 0) || (r.z < thr);
@@ -324,7 +338,7 @@ __global__ void __launch_bounds__(128, MCQ_SPEC_MINB) spec_kernel(const __grid_c
             const unsigned nearm = __ballot_sync(FULLMASK, near_flag && valid) & committed;
             const unsigned badm = __ballot_sync(FULLMASK, bad && valid) & committed;
             if (lane == 0) {
-                rec[R_NEAR] += __popc(nearm);
+                SM32(sR + R_NEAR) += (uint32_t)__popc(nearm);
                 if (badm) atomicAdd(a.replay_err, (unsigned)__popc(badm));
             }
         }
@@ -336,66 +350,60 @@ __global__ void __launch_bounds__(128, MCQ_SPEC_MINB) spec_kernel(const __grid_c
         }
         // acceptance bins: close every bin that ends at or before the last consumed step
         if (t + adv - 1 >= next_edge) {
-            int bin = rec[R_BIN];
-            const int n_acc = rec[R_NACC];
+            int bin = (int)SM32(sR + R_BIN);
+            __syncwarp();
             while (t + adv - 1 >= next_edge) {
                 if (lane == 0) {
-                    if (a.acc_hist) a.acc_hist[(size_t)chain * a.n_bins + bin] = (uint32_t)(n_acc - rec[R_BIN_MARK]);
-                    rec[R_BIN_MARK] = n_acc;
+                    if (a.acc_hist) a.acc_hist[(size_t)chain * a.n_bins + bin] = (uint32_t)n_acc - SM32(sR + R_BIN_MARK);
+                    SM32(sR + R_BIN_MARK) = (uint32_t)n_acc;
                 }
                 ++bin;
                 next_edge = a.bin_starts[bin + 1];
             }
-            if (lane == 0) rec[R_BIN] = bin;
+            if (lane == 0) SM32(sR + R_BIN) = (uint32_t)bin;
             __syncwarp();
         }
         if (first >= 0) {
             const uint32_t wc0 = __shfl_sync(FULLMASK, c0, first);
             const uint32_t wc1 = __shfl_sync(FULLMASK, c1, first);
             const uint32_t waux = __shfl_sync(FULLMASK, aux, first);
-            table_lines_add(T, a.nbr + (size_t)wc0 * L, rounds, lane, -1);
-            if (lane == 0) T[wc0] = (uint8_t)(T[wc0] - NF);
+            table_lines_add(sT, a.nbr + (size_t)wc0 * L, rounds, lane, -1);
+            if (lane == 0) SM8(sT + wc0) = (unsigned char)(SM8(sT + wc0) - NF);
             __syncwarp();
-            table_lines_add(T, a.nbr + (size_t)wc1 * L, rounds, lane, +1);
+            table_lines_add(sT, a.nbr + (size_t)wc1 * L, rounds, lane, +1);
+            const int ta = t + first;
             if (lane == 0) {
-                T[wc1] = (uint8_t)(T[wc1] + NF);
+                SM8(sT + wc1) = (unsigned char)(SM8(sT + wc1) + NF);
                 if (FULL) {
-                    occ[wc0 >> 5] &= ~(1u << (wc0 & 31));
-                    occ[wc1 >> 5] |= 1u << (wc1 & 31);
-                    pos[waux & 0xffffu] = wc1 | (waux & 0xffff0000u);
+                    SM32(sO + 4 * (wc0 >> 5)) &= ~(1u << (wc0 & 31));
+                    SM32(sO + 4 * (wc1 >> 5)) |= 1u << (wc1 & 31);
+                    SM32(sP + 4 * (waux & 0xffffu)) = wc1 | (waux & 0xffff0000u);
                 } else {
-                    st[waux & 0xffffu] = (unsigned char)(waux >> 16);
+                    SM8(sP + (waux & 0xffffu)) = (unsigned char)(waux >> 16);
                 }
-                // accept bookkeeping lives with lane 0
-                const int ta = t + first;
-                rec[R_NACC] += 1;
-                if ((ta >> 5) != rec[R_ACC_BLK]) {
-                    if (rec[R_ACCBITS] && a.abits) a.abits[(size_t)chain * a.abits_pitch + rec[R_ACC_BLK]] = (uint32_t)rec[R_ACCBITS];
-                    rec[R_ACC_BLK] = ta >> 5;
-                    rec[R_ACCBITS] = 0;
-                }
-                rec[R_ACCBITS] |= (int)(1u << (ta & 31));
-                if (improved && !stop) rec[R_BEST_STEP] = ta + 1;
+                if (abits_row) atomicOr(abits_row + (ta >> 5), 1u << (ta & 31));
+                if (improved && !stop) SM32(sR + R_BEST_STEP) = (uint32_t)(ta + 1);
             }
             __syncwarp();
             E = E_new;
+            ++n_acc;
             if (improved) {
                 // snapshot: the state at the first visit of the minimum (strict <, :252 / :340)
                 best = E;
                 uint8_t *bs = a.best_state + (size_t)chain * a.state_bytes;
                 if (FULL) {
                     for (int qi = lane; qi < a.Q; qi += 32) {
-                        const int c = (int)(pos[qi] & 0xffffu);
+                        const int c = (int)(SM32(sP + 4 * qi) & 0xffffu);
                         bs[3 * qi] = (uint8_t)(c / (N * N)); bs[3 * qi + 1] = (uint8_t)((c / N) % N); bs[3 * qi + 2] = (uint8_t)(c % N);
                     }
                 } else {
-                    for (int c = lane; c < a.Q; c += 32) bs[c] = st[c];
+                    for (int c = lane; c < a.Q; c += 32) bs[c] = SM8(sP + c);
                 }
             }
         }
         if (stop) {
             done = t + adv - 1;
-            if (lane == 0 && a.acc_hist) a.acc_hist[(size_t)chain * a.n_bins + rec[R_BIN]] = (uint32_t)(rec[R_NACC] - rec[R_BIN_MARK]);
+            if (lane == 0 && a.acc_hist) a.acc_hist[(size_t)chain * a.n_bins + SM32(sR + R_BIN)] = (uint32_t)n_acc - SM32(sR + R_BIN_MARK);
             break;
         }
         t += adv;
@@ -404,27 +412,30 @@ __global__ void __launch_bounds__(128, MCQ_SPEC_MINB) spec_kernel(const __grid_c
     // ---------------- write the record back ----------------
     __syncwarp();
     if (lane == 0) {
-        if (rec[R_ACCBITS] && a.abits) a.abits[(size_t)chain * a.abits_pitch + rec[R_ACC_BLK]] = (uint32_t)rec[R_ACCBITS];
         if (a.t_end == a.n_steps && a.n_bins > 0 && a.acc_hist && done == a.t_end)
-            a.acc_hist[(size_t)chain * a.n_bins + rec[R_BIN]] = (uint32_t)(rec[R_NACC] - rec[R_BIN_MARK]);
+            a.acc_hist[(size_t)chain * a.n_bins + SM32(sR + R_BIN)] = (uint32_t)n_acc - SM32(sR + R_BIN_MARK);
         a.cur_e[chain] = E;
         a.best_e[chain] = best;
-        a.best_step[chain] = rec[R_BEST_STEP];
-        a.n_acc[chain] = rec[R_NACC];
+        a.best_step[chain] = (int)SM32(sR + R_BEST_STEP);
+        a.n_acc[chain] = n_acc;
         a.stale[chain] = stale;
-        a.bin_mark[chain] = rec[R_BIN_MARK];
+        a.bin_mark[chain] = (int)SM32(sR + R_BIN_MARK);
         a.steps_done[chain] = done;
-        if (REPLAY && a.near_cnt) a.near_cnt[chain] += (uint32_t)rec[R_NEAR];
+        if (REPLAY && a.near_cnt) a.near_cnt[chain] += SM32(sR + R_NEAR);
     }
     uint8_t *out = a.state + (size_t)chain * a.state_bytes;
     if (FULL) {
         for (int qi = lane; qi < a.Q; qi += 32) {
-            const int c = (int)(pos[qi] & 0xffffu);
+            const int c = (int)(SM32(sP + 4 * qi) & 0xffffu);
             out[3 * qi] = (uint8_t)(c / (N * N)); out[3 * qi + 1] = (uint8_t)((c / N) % N); out[3 * qi + 2] = (uint8_t)(c % N);
         }
     } else {
-        for (int c = lane; c < a.Q; c += 32) out[c] = st[c];
+        for (int c = lane; c < a.Q; c += 32) out[c] = SM8(sP + c);
     }
 }
+
+#undef SM8
+#undef SM16
+#undef SM32
 
 }  // namespace mcq
