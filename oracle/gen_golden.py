@@ -179,10 +179,57 @@ REPLAYS = [
 ]
 
 
+POOLS = [
+    # mode, N, n_steps, n_chains, base_seed  (linear 1->3, random init)
+    ("board", 8, 10000, 200, 1000),
+    ("full_3d", 8, 10000, 200, 2000),
+    ("board", 12, 20000, 64, 3000),
+    ("full_3d", 12, 20000, 64, 4000),
+]
+
+
+def _pool_chain(args):
+    mode, n, n_steps, seed = args
+    exp, _, _ = ref_harness.load_reference()
+    sched = exp.build_schedule_from_params("linear_annealing", n_steps, beta_start=1.0, beta_end=3.0)
+    fn = exp.metropolis_mcmc_board if mode == "board" else exp.metropolis_mcmc
+    with _quiet():
+        r = fn(n, n_steps, "random", sched, verbose=False, seed=seed)
+    h = np.asarray(r["energy_history"])
+    acc = np.zeros(n_steps, dtype=np.int64)
+    acc[np.asarray(r["accepted_steps"], dtype=np.int64)] = 1
+    edges = np.ceil(np.linspace(0, n_steps, 101)).astype(int)
+    return (int(h[0]), int(r["best_energy"]), int(r["final_energy"]), len(r["accepted_steps"]), int(r["steps_to_best"]),
+            np.add.reduceat(acc, edges[:-1]), h[:: n_steps // 20])
+
+
+def pools():
+    """Distributions of the reference's chain outputs under its own RNG, for statistical parity."""
+    from concurrent.futures import ProcessPoolExecutor
+    out = {}
+    with ProcessPoolExecutor() as ex:
+        for mode, n, n_steps, n_chains, base_seed in POOLS:
+            res = list(ex.map(_pool_chain, [(mode, n, n_steps, base_seed + c) for c in range(n_chains)]))
+            key = f"{mode}_N{n}"
+            out[f"{key}_n_steps"] = np.int64(n_steps)
+            out[f"{key}_E0"] = np.array([r[0] for r in res])
+            out[f"{key}_best"] = np.array([r[1] for r in res])
+            out[f"{key}_final"] = np.array([r[2] for r in res])
+            out[f"{key}_n_acc"] = np.array([r[3] for r in res])
+            out[f"{key}_steps_to_best"] = np.array([r[4] for r in res])
+            out[f"{key}_acc_bins"] = np.sum([r[5] for r in res], axis=0)
+            out[f"{key}_mean_curve"] = np.mean([r[6] for r in res], axis=0)
+            print(key, "best mean", out[f"{key}_best"].mean(), "acc mean", out[f"{key}_n_acc"].mean())
+    np.savez_compressed(os.path.join(OUT, "pools.npz"), **out)
+
+
 def main():
     if not ref_harness.reference_available():
         sys.exit("reference tree not present; golden fixtures can only be generated in the authoring container")
     os.makedirs(OUT, exist_ok=True)
+    if "--pools-only" in sys.argv:
+        pools()
+        return
     exp, mcmc, mcmc_board = ref_harness.load_reference()
     kat = kat_tables(exp, mcmc, mcmc_board)
     kat["config_c1"] = config_c1(exp)
@@ -198,6 +245,7 @@ def main():
         np.savez_compressed(os.path.join(OUT, f"replay_{mode}_N{n}_{init}_{sched}.npz"), **rec)
         print(f"replay {mode} N={n} {init} {sched}: E0={rec['history'][0]} best={rec['best_energy']} "
               f"acc={int(rec['accepted'].sum())}")
+    pools()
     print("golden fixtures written to", OUT)
 
 

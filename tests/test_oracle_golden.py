@@ -1,0 +1,139 @@
+"""CPU: the oracles (NumPy restatement, C restatement) against fixtures produced by the REAL reference."""
+import glob
+import math
+import os
+from concurrent.futures import ProcessPoolExecutor
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, SCHEDS, replay_files
+from oracle import c_oracle
+from oracle import queens_numpy as qn
+
+
+def test_deterministic_init_energies(kat):
+    for n in range(2, 21):
+        assert [qn.energy_board(qn.init_board(n, "latin")), qn.energy_full(qn.init_full(n, "latin"))] == kat["latin_energy"][str(n)]
+        np.random.seed(0)
+        b = qn.energy_board(qn.init_board(n, "klarner"))
+        np.random.seed(0)
+        f = qn.energy_full(qn.init_full(n, "klarner"))
+        assert [b, f] == kat["klarner_energy_seed0"][str(n)]
+        if math.gcd(n, 210) == 1:
+            assert b == 0 and f == 0
+
+
+def test_seeded_random_init(kat):
+    for n, want in kat["random_init_seed42"].items():
+        n = int(n)
+        np.random.seed(42)
+        h = qn.init_board(n, "random")
+        np.random.seed(42)
+        c = qn.init_full(n, "random")
+        assert qn.energy_board(h) == want["board_energy"] and qn.energy_full(c) == want["full_energy"]
+        assert h[0].tolist() == want["board_heights_row0"] and c[:4].tolist() == want["full_queens_first4"]
+
+
+def test_energy_and_conflict_fixtures(energy_cases):
+    for n in list(range(2, 21)) + [32]:
+        for h, e in zip(energy_cases[f"board_heights_{n}"], energy_cases[f"board_energy_{n}"]):
+            assert qn.energy_board(h) == e == c_oracle.energy("board", h)
+            assert qn.energy_by_lines(n, qn.board_cells(h), with_column=False) == e
+        for c, e in zip(energy_cases[f"full_cells_{n}"], energy_cases[f"full_energy_{n}"]):
+            assert qn.energy_full(c) == e == c_oracle.energy("full_3d", c)
+            assert qn.energy_by_lines(n, c) == e
+    for n in (3, 5, 8, 12, 15):
+        h = energy_cases[f"delta_board_state_{n}"]
+        for i, j, k, before, after in energy_cases[f"delta_board_moves_{n}"]:
+            assert qn.conflicts_board(h, i, j, h[i, j]) == before and qn.conflicts_board(h, i, j, k) == after
+        c = energy_cases[f"delta_full_state_{n}"]
+        for q, i, j, k, before, after in energy_cases[f"delta_full_moves_{n}"]:
+            assert qn.conflicts_full(c, q) == before and qn.conflicts_full(c, q, (i, j, k)) == after
+
+
+def test_schedule_closures(kat):
+    for n_steps, entry in kat["schedules"].items():
+        n_steps = int(n_steps)
+        for name, p in SCHEDS.items():
+            f = qn.schedule_from_params(p, n_steps)
+            assert [float(f(s)).hex() for s in entry["steps"]] == entry[name], (name, n_steps)
+    with pytest.raises(ValueError):
+        qn.make_beta_schedule("geometric", 10, beta_start=1, beta_end=2)
+
+
+def _rerun(path):
+    g = np.load(path)
+    sched = qn.schedule_from_params(SCHEDS[str(g["sched_name"])], int(g["n_steps"]))
+    r = qn.run_chain(str(g["mode"]), int(g["n"]), int(g["n_steps"]), str(g["init_mode"]), sched, seed=int(g["seed"]))
+    acc = np.zeros(int(g["n_steps"]), dtype=np.uint8)
+    acc[np.asarray(r["accepted_steps"], dtype=np.int64)] = 1
+    return (np.asarray(r["energy_history"]).tolist() == g["history"].tolist()
+            and acc.tolist() == g["accepted"].tolist()
+            and np.asarray(r["final_state"]).tolist() == g["final_state"].tolist()
+            and np.asarray(r["best_state"]).tolist() == g["best_state"].tolist()
+            and r["steps_to_best"] == int(g["steps_to_best"]) and r["best_energy"] == int(g["best_energy"]))
+
+
+def test_numpy_oracle_reproduces_reference_chains_from_the_seed():
+    """Same legacy-RNG call order => the reference's trajectory, bit for bit."""
+    with ProcessPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+        ok = list(ex.map(_rerun, replay_files()))
+    assert all(ok), [os.path.basename(p) for p, o in zip(replay_files(), ok) if not o]
+
+
+@pytest.mark.parametrize("path", replay_files(), ids=lambda p: os.path.basename(p)[7:-4])
+def test_c_oracle_replays_reference_streams(path):
+    g = np.load(path)
+    r = c_oracle.replay(str(g["mode"]), int(g["n"]), g["init_state"], g["moves"], g["uniforms"], g["betas"])
+    assert r["history"].tolist() == g["history"].tolist()
+    assert r["accepted"].tolist() == g["accepted"].tolist()
+    assert r["final_state"].tolist() == g["final_state"].tolist()
+    assert r["best_state"].tolist() == g["best_state"].tolist()
+    assert (r["steps_to_best"], r["best_energy"], r["final_energy"]) == (int(g["steps_to_best"]), int(g["best_energy"]), int(g["final_energy"]))
+
+
+def _c1_chain(seed):
+    sched = qn.schedule_from_params(SCHEDS["linear"], 100000)
+    r = qn.chain_board(8, 100000, "random", sched, seed=seed)
+    h = r["energy_history"]
+    return r["best_energy"], r["steps_to_best"], len(r["accepted_steps"]), h[0], h[-1], len(h)
+
+
+def test_config_c1_known_answers(kat):
+    """BASELINE config C1 (N=8 board, 10 runs x 1e5 steps, seeds 42..51): three of the ten chains here
+    (the full set is a 35 s job on 8 cores; every chain is an independent seed)."""
+    c1 = kat["config_c1"]
+    picks = [0, 3, 9]
+    with ProcessPoolExecutor(max_workers=3) as ex:
+        res = list(ex.map(_c1_chain, [42 + i for i in picks]))
+    for i, (best, s2b, nacc, e0, fin, ln) in zip(picks, res):
+        assert (best, s2b, nacc, e0, fin, ln) == (c1["best_energies"][i], c1["steps_to_best"][i], c1["accept_counts"][i],
+                                                   c1["E0"][i], c1["final"][i], c1["history_len"])
+
+
+def test_c_generator_is_self_consistent():
+    rng = np.random.RandomState(3)
+    for mode, n in (("board", 9), ("full_3d", 7)):
+        st = rng.randint(0, n, size=(n, n)) if mode == "board" else qn.init_full(n, "latin")
+        betas = np.linspace(0.5, 3.0, 3000)
+        g = c_oracle.generate(mode, n, st, betas, seed=11)
+        r = c_oracle.replay(mode, n, st, g["moves"], g["uniforms"], betas)
+        assert r["history"].tolist() == g["history"].tolist()
+        e = qn.energy_board(g["final_state"]) if mode == "board" else qn.energy_full(g["final_state"])
+        assert e == g["final_energy"] == g["history"][-1]
+        assert int(np.argmin(g["history"])) == g["steps_to_best"]
+        # the NumPy restatement walks the same recorded stream to the same energies
+        h = np.array(st)
+        cur = g["history"][0]
+        for step, ((a, b, c, d), acc) in enumerate(zip(g["moves"][:200], g["accepted"][:200])):
+            if mode == "board":
+                delta = qn.conflicts_board(h, a, b, c) - qn.conflicts_board(h, a, b)
+                if acc:
+                    h[a, b] = c
+            else:
+                delta = qn.conflicts_full(h, a, (b, c, d)) - qn.conflicts_full(h, a)
+                if acc:
+                    h[a] = (b, c, d)
+            cur += delta if acc else 0
+            assert cur == g["history"][step + 1]
