@@ -293,19 +293,34 @@ static cudaError_t launch_g(const KArgs &a, bool replay, int grid, int block, si
     return replay ? launch_one<G, false, true>(a, grid, block, smem, s) : launch_one<G, false, false>(a, grid, block, smem, s);
 }
 
-template <bool FULL, bool REPLAY, bool EARLY>
+template <bool FULL, bool REPLAY, bool EARLY, int NR>
 static cudaError_t launch_spec_one(const KArgs &a, int grid, int block, size_t smem, cudaStream_t s) {
-    auto k = spec_kernel<FULL, REPLAY, EARLY>;
+    auto k = spec_kernel<FULL, REPLAY, EARLY, NR>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     k<<<grid, block, smem, s>>>(a);
     return cudaGetLastError();
 }
 
+// production kernels have the neighbour-row length compiled in; replay / early-stop ones take it at run time
+template <bool FULL>
+static cudaError_t launch_spec_nr(const KArgs &a, int grid, int block, size_t smem, cudaStream_t s) {
+    switch (a.sl.rounds) {
+        case 1: return launch_spec_one<FULL, false, false, 1>(a, grid, block, smem, s);
+        case 2: return launch_spec_one<FULL, false, false, 2>(a, grid, block, smem, s);
+        case 3: return launch_spec_one<FULL, false, false, 3>(a, grid, block, smem, s);
+        case 4: return launch_spec_one<FULL, false, false, 4>(a, grid, block, smem, s);
+        case 5: return launch_spec_one<FULL, false, false, 5>(a, grid, block, smem, s);
+        case 6: return launch_spec_one<FULL, false, false, 6>(a, grid, block, smem, s);
+        case 7: return launch_spec_one<FULL, false, false, 7>(a, grid, block, smem, s);
+        default: return launch_spec_one<FULL, false, false, 8>(a, grid, block, smem, s);
+    }
+}
+
 static cudaError_t launch_spec(const KArgs &a, bool replay, int grid, int block, size_t smem, cudaStream_t s) {
-    if (a.full) return replay ? launch_spec_one<true, true, false>(a, grid, block, smem, s) : launch_spec_one<true, false, false>(a, grid, block, smem, s);
-    if (a.patience >= 0) return replay ? launch_spec_one<false, true, true>(a, grid, block, smem, s) : launch_spec_one<false, false, true>(a, grid, block, smem, s);
-    return replay ? launch_spec_one<false, true, false>(a, grid, block, smem, s) : launch_spec_one<false, false, false>(a, grid, block, smem, s);
+    if (a.full) return replay ? launch_spec_one<true, true, false, 0>(a, grid, block, smem, s) : launch_spec_nr<true>(a, grid, block, smem, s);
+    if (a.patience >= 0) return replay ? launch_spec_one<false, true, true, 0>(a, grid, block, smem, s) : launch_spec_one<false, false, true, 0>(a, grid, block, smem, s);
+    return replay ? launch_spec_one<false, true, false, 0>(a, grid, block, smem, s) : launch_spec_nr<false>(a, grid, block, smem, s);
 }
 
 static cudaError_t launch_anneal(int G, const KArgs &a, bool replay, int grid, int block, size_t smem, cudaStream_t s) {

@@ -102,32 +102,68 @@ __global__ void build_wide_lut_kernel(int N, uint16_t *wide, uint32_t *lut, int 
 
 // ---- shared memory is addressed by 32-bit byte offsets into the dynamic array -----------------
 // (no generic pointers: one base register per slab instead of 64-bit pointer pairs)
+// Explicit shared-state-space accesses on 32-bit addresses: one base register per slab, and no
+// generic-pointer arithmetic in the loop.
 extern __shared__ __align__(16) unsigned char smem[];
-#define SM8(off) (smem[(off)])
-#define SM16(off) (*reinterpret_cast<uint16_t *>(smem + (off)))
-#define SM32(off) (*reinterpret_cast<uint32_t *>(smem + (off)))
 
-// T[c] += delta for every cell c on the attack lines through one cell (its neighbour row of NR*32
-// ids).  sT = byte offset of the chain's table.  All lanes must call.
+template <typename T>
+struct SmRef {
+    uint32_t addr;   // shared-window address in bytes
+    __device__ __forceinline__ operator T() const {
+        uint32_t v;
+        if constexpr (sizeof(T) == 1) asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+        else if constexpr (sizeof(T) == 2) asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr));
+        else asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+        return (T)v;
+    }
+    __device__ __forceinline__ const SmRef &operator=(T x) const {
+        const uint32_t v = (uint32_t)x;
+        if constexpr (sizeof(T) == 1) asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+        else if constexpr (sizeof(T) == 2) asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+        else asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+        return *this;
+    }
+    __device__ __forceinline__ const SmRef &operator+=(T x) const { return *this = (T)((T) * this + x); }
+    __device__ __forceinline__ const SmRef &operator&=(T x) const { return *this = (T)((T) * this & x); }
+    __device__ __forceinline__ const SmRef &operator|=(T x) const { return *this = (T)((T) * this | x); }
+};
+__device__ __forceinline__ void sm_red_or(uint32_t addr, uint32_t bits) {
+    asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(addr), "r"(bits) : "memory");
+}
+#define SM8(off) (SmRef<unsigned char>{sbase + (uint32_t)(off)})
+#define SM16(off) (SmRef<uint16_t>{sbase + (uint32_t)(off)})
+#define SM32(off) (SmRef<uint32_t>{sbase + (uint32_t)(off)})
+
+// T[c] += delta for every cell c on the attack lines through one cell: its neighbour row of NR*32
+// ids starting at element `row` of nbr.  aT = shared address of the chain's table.  All lanes call.
 template <int NR>
-__device__ __forceinline__ void table_row_add(int sT, const uint16_t *row, int lane, int delta) {
-    int c[NR];
+__device__ __forceinline__ void table_row_add(uint32_t aT, const uint16_t *nbr, uint32_t row, int delta) {
+    uint32_t c[NR];
 #pragma unroll
-    for (int r = 0; r < NR; ++r) c[r] = __ldg(row + r * 32 + lane);
+    for (int r = 0; r < NR; ++r) c[r] = __ldg(nbr + row + r * 32);
 #pragma unroll
-    for (int r = 0; r < NR; ++r) SM8(sT + c[r]) = (unsigned char)(SM8(sT + c[r]) + delta);
+    for (int r = 0; r < NR; ++r) {
+        const SmRef<unsigned char> cell{aT + c[r]};
+        cell = (unsigned char)((unsigned char)cell + delta);
+    }
 }
 
-__device__ __forceinline__ void table_lines_add(int sT, const uint16_t *row, int nr, int lane, int delta) {
-    switch (nr) {
-        case 1: table_row_add<1>(sT, row, lane, delta); break;
-        case 2: table_row_add<2>(sT, row, lane, delta); break;
-        case 3: table_row_add<3>(sT, row, lane, delta); break;
-        case 4: table_row_add<4>(sT, row, lane, delta); break;
-        case 5: table_row_add<5>(sT, row, lane, delta); break;
-        case 6: table_row_add<6>(sT, row, lane, delta); break;
-        case 7: table_row_add<7>(sT, row, lane, delta); break;
-        default: table_row_add<8>(sT, row, lane, delta); break;
+// NR == 0: row length known at run time only (replay kernels); otherwise compiled in.
+template <int NR>
+__device__ __forceinline__ void table_lines_add(uint32_t aT, const uint16_t *nbr, uint32_t row, int nr, int delta) {
+    if constexpr (NR > 0) {
+        table_row_add<NR>(aT, nbr, row, delta);
+    } else {
+        switch (nr) {
+            case 1: table_row_add<1>(aT, nbr, row, delta); break;
+            case 2: table_row_add<2>(aT, nbr, row, delta); break;
+            case 3: table_row_add<3>(aT, nbr, row, delta); break;
+            case 4: table_row_add<4>(aT, nbr, row, delta); break;
+            case 5: table_row_add<5>(aT, nbr, row, delta); break;
+            case 6: table_row_add<6>(aT, nbr, row, delta); break;
+            case 7: table_row_add<7>(aT, nbr, row, delta); break;
+            default: table_row_add<8>(aT, nbr, row, delta); break;
+        }
     }
 }
 
@@ -140,11 +176,12 @@ __device__ __forceinline__ float ex2_approx(float x) {
 // lane-0 scalars kept in the slab instead of registers (byte offsets from sl.off_rec)
 enum RecSlot { R_BEST_STEP = 0, R_BIN_MARK = 4, R_BIN = 8, R_NEAR = 12 };
 
-template <bool FULL, bool REPLAY, bool EARLY>
+template <bool FULL, bool REPLAY, bool EARLY, int NR>
 __global__ void __launch_bounds__(128, MCQ_SPEC_MINB) spec_kernel(const __grid_constant__ KArgs a) {
     constexpr unsigned FULLMASK = 0xffffffffu;
     constexpr int NF = FULL ? NFAM : NFAM - 1;
     const int lane = threadIdx.x & 31;
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem);
     const int N = a.N;
 
     // ---- CTA-shared geometry: shared-line bits at offset 0, cell -> wide id at sl.off_wide ----
@@ -171,7 +208,7 @@ __global__ void __launch_bounds__(128, MCQ_SPEC_MINB) spec_kernel(const __grid_c
         if (FULL) {
             const int cid = ((int)ext[3 * qi] * N + (int)ext[3 * qi + 1]) * N + (int)ext[3 * qi + 2];
             SM32(sP + 4 * qi) = (uint32_t)cid | ((uint32_t)SM16(sW + 2 * cid) << 16);
-            atomicOr(&SM32(sO + 4 * (cid >> 5)), 1u << (cid & 31));
+            sm_red_or(sbase + (uint32_t)(sO + 4 * (cid >> 5)), 1u << (cid & 31));
         } else {
             SM8(sP + qi) = ext[qi];
         }
@@ -179,7 +216,7 @@ __global__ void __launch_bounds__(128, MCQ_SPEC_MINB) spec_kernel(const __grid_c
     __syncwarp();
     for (int qi = 0; qi < a.Q; ++qi) {
         const int c = FULL ? (int)(SM32(sP + 4 * qi) & 0xffffu) : qi * N + (int)SM8(sP + qi);
-        table_lines_add(sT, a.nbr + (size_t)c * L, rounds, lane, 1);
+        table_lines_add<NR>(sbase + (uint32_t)sT, a.nbr, (uint32_t)(c * L + lane), rounds, 1);
         if (lane == 0) SM8(sT + c) = (unsigned char)(SM8(sT + c) + NF);
         __syncwarp();
     }
@@ -367,10 +404,10 @@ __global__ void __launch_bounds__(128, MCQ_SPEC_MINB) spec_kernel(const __grid_c
             const uint32_t wc0 = __shfl_sync(FULLMASK, c0, first);
             const uint32_t wc1 = __shfl_sync(FULLMASK, c1, first);
             const uint32_t waux = __shfl_sync(FULLMASK, aux, first);
-            table_lines_add(sT, a.nbr + (size_t)wc0 * L, rounds, lane, -1);
+            table_lines_add<NR>(sbase + (uint32_t)sT, a.nbr, wc0 * (uint32_t)L + (uint32_t)lane, rounds, -1);
             if (lane == 0) SM8(sT + wc0) = (unsigned char)(SM8(sT + wc0) - NF);
             __syncwarp();
-            table_lines_add(sT, a.nbr + (size_t)wc1 * L, rounds, lane, +1);
+            table_lines_add<NR>(sbase + (uint32_t)sT, a.nbr, wc1 * (uint32_t)L + (uint32_t)lane, rounds, +1);
             const int ta = t + first;
             if (lane == 0) {
                 SM8(sT + wc1) = (unsigned char)(SM8(sT + wc1) + NF);
