@@ -61,7 +61,8 @@ struct SLayout {
 struct KArgs {
     int full;  // 0 board, 1 full_3d
     int N, Q;
-    int n_chains;
+    int n_chains;         // one past the last chain of this launch (absolute index)
+    int chain_begin;      // first chain of this launch: CTA 0 starts here
     int n_steps;          // total steps of the schedule (row length of the beta tables)
     int t_begin, t_end;   // this launch covers steps [t_begin, t_end)
     int patience;         // < 0: none
@@ -236,7 +237,7 @@ __global__ void __launch_bounds__(256) anneal_kernel(const __grid_constant__ KAr
     const int g = tid & (G - 1);
     const int cl = tid / G;
     const int cpc = blockDim.x / G;
-    const int chain = blockIdx.x * cpc + cl;
+    const int chain = a.chain_begin + blockIdx.x * cpc + cl;
     const bool live = chain < a.n_chains;
     const int N = a.N;
     const int PB = a.lay.pb;

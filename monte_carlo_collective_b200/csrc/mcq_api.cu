@@ -6,9 +6,11 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
+#include <cmath>
 #include <map>
 #include <string>
 #include <vector>
@@ -270,6 +272,7 @@ struct mcq_ctx {
     int device;
     cudaStream_t stream;
     cudaStream_t copy_stream;
+    cudaStream_t sub_stream[4];
     cudaDeviceProp prop;
     mcq::DevBuf buf[mcq::B_NBUF];
     std::map<int, mcq::DevBuf> nbr;   // neighbour lists per (mode, N), built on first use
@@ -293,9 +296,9 @@ static cudaError_t launch_g(const KArgs &a, bool replay, int grid, int block, si
     return replay ? launch_one<G, false, true>(a, grid, block, smem, s) : launch_one<G, false, false>(a, grid, block, smem, s);
 }
 
-template <bool FULL, bool REPLAY, bool EARLY, int NR>
+template <bool FULL, bool REPLAY, bool EARLY, int NR, int LPC>
 static cudaError_t launch_spec_one(const KArgs &a, int grid, int block, size_t smem, cudaStream_t s) {
-    auto k = spec_kernel<FULL, REPLAY, EARLY, NR>;
+    auto k = spec_kernel<FULL, REPLAY, EARLY, NR, LPC>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     k<<<grid, block, smem, s>>>(a);
@@ -303,24 +306,29 @@ static cudaError_t launch_spec_one(const KArgs &a, int grid, int block, size_t s
 }
 
 // production kernels have the neighbour-row length compiled in; replay / early-stop ones take it at run time
-template <bool FULL>
+template <bool FULL, int LPC>
 static cudaError_t launch_spec_nr(const KArgs &a, int grid, int block, size_t smem, cudaStream_t s) {
     switch (a.sl.rounds) {
-        case 1: return launch_spec_one<FULL, false, false, 1>(a, grid, block, smem, s);
-        case 2: return launch_spec_one<FULL, false, false, 2>(a, grid, block, smem, s);
-        case 3: return launch_spec_one<FULL, false, false, 3>(a, grid, block, smem, s);
-        case 4: return launch_spec_one<FULL, false, false, 4>(a, grid, block, smem, s);
-        case 5: return launch_spec_one<FULL, false, false, 5>(a, grid, block, smem, s);
-        case 6: return launch_spec_one<FULL, false, false, 6>(a, grid, block, smem, s);
-        case 7: return launch_spec_one<FULL, false, false, 7>(a, grid, block, smem, s);
-        default: return launch_spec_one<FULL, false, false, 8>(a, grid, block, smem, s);
+        case 1: return launch_spec_one<FULL, false, false, 1, LPC>(a, grid, block, smem, s);
+        case 2: return launch_spec_one<FULL, false, false, 2, LPC>(a, grid, block, smem, s);
+        case 3: return launch_spec_one<FULL, false, false, 3, LPC>(a, grid, block, smem, s);
+        case 4: return launch_spec_one<FULL, false, false, 4, LPC>(a, grid, block, smem, s);
+        case 5: return launch_spec_one<FULL, false, false, 5, LPC>(a, grid, block, smem, s);
+        case 6: return launch_spec_one<FULL, false, false, 6, LPC>(a, grid, block, smem, s);
+        case 7: return launch_spec_one<FULL, false, false, 7, LPC>(a, grid, block, smem, s);
+        default: return launch_spec_one<FULL, false, false, 8, LPC>(a, grid, block, smem, s);
     }
 }
 
-static cudaError_t launch_spec(const KArgs &a, bool replay, int grid, int block, size_t smem, cudaStream_t s) {
-    if (a.full) return replay ? launch_spec_one<true, true, false, 0>(a, grid, block, smem, s) : launch_spec_nr<true>(a, grid, block, smem, s);
-    if (a.patience >= 0) return replay ? launch_spec_one<false, true, true, 0>(a, grid, block, smem, s) : launch_spec_one<false, false, true, 0>(a, grid, block, smem, s);
-    return replay ? launch_spec_one<false, true, false, 0>(a, grid, block, smem, s) : launch_spec_nr<false>(a, grid, block, smem, s);
+template <int LPC>
+static cudaError_t launch_spec_lpc(const KArgs &a, bool replay, int grid, int block, size_t smem, cudaStream_t s) {
+    if (a.full) return replay ? launch_spec_one<true, true, false, 0, LPC>(a, grid, block, smem, s) : launch_spec_nr<true, LPC>(a, grid, block, smem, s);
+    if (a.patience >= 0) return replay ? launch_spec_one<false, true, true, 0, LPC>(a, grid, block, smem, s) : launch_spec_one<false, false, true, 0, LPC>(a, grid, block, smem, s);
+    return replay ? launch_spec_one<false, true, false, 0, LPC>(a, grid, block, smem, s) : launch_spec_nr<false, LPC>(a, grid, block, smem, s);
+}
+
+static cudaError_t launch_spec(int lpc, const KArgs &a, bool replay, int grid, int block, size_t smem, cudaStream_t s) {
+    return lpc == 16 ? launch_spec_lpc<16>(a, replay, grid, block, smem, s) : launch_spec_lpc<32>(a, replay, grid, block, smem, s);
 }
 
 static cudaError_t launch_anneal(int G, const KArgs &a, bool replay, int grid, int block, size_t smem, cudaStream_t s) {
@@ -391,6 +399,7 @@ int mcq_create(int device, mcq_ctx **out) {
     }
     CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    for (auto &ss : c->sub_stream) CUDA_TRY(cudaStreamCreateWithFlags(&ss, cudaStreamNonBlocking));
     *out = c;
     return 0;
 }
@@ -403,6 +412,7 @@ int mcq_destroy(mcq_ctx *ctx) {
     for (auto &kv : ctx->geo) kv.second.release();
     cudaStreamDestroy(ctx->stream);
     cudaStreamDestroy(ctx->copy_stream);
+    for (auto ss : ctx->sub_stream) cudaStreamDestroy(ss);
     delete ctx;
     return 0;
 }
@@ -573,19 +583,50 @@ int mcq_run(mcq_ctx *ctx, const mcq_run_params *p) {
     int grid = (nc + cpc - 1) / cpc;
     size_t smem = (size_t)cpc * lay.stride;
     const SLayout sl = make_spec_layout(full, p->n, p->q);
-    if (use_spec) {   // one warp per chain; the register file bounds residency, not shared memory
+    int spec_lpc = 32;
+    if (use_spec) {
+        // Lane groups of 16 or 32 per chain.  Registers (64/thread) allow 32 warps per SM; shared memory may allow
+        // fewer.  All CTAs of a launch take the same time, so a launch costs ceil(waves) full waves: pick the
+        // (group width, resident CTAs per SM) pair with the best modelled rate x wave efficiency.
         if (wpc > 4) return fail(MCQ_EINVAL, "the conflict-table kernel runs at most 4 warps per CTA");
         const int w = wpc ? wpc : 4;
-        cpc = w;
+        const int sms = ctx->prop.multiProcessorCount;
+        auto cta_smem = [&](int lpc) { return (size_t)sl.cta_bytes + (size_t)w * (32 / lpc) * sl.stride; };
+        auto max_ctas = [&](int lpc) {   // residency limit: registers, warps, shared memory
+            const size_t need = cta_smem(lpc);
+            if (need > smem_block) return 0;
+            return (int)std::min<size_t>((size_t)(32 / w), smem_sm / (round_up((int)need, 1024) + 1024));
+        };
+        // relative throughput of one SM vs resident warps (measured, N=12 full_3d, single full wave)
+        auto rate = [&](int lpc, int warps) {
+            static const float r32[] = {0.0f, 0.40f, 0.80f, 0.967f, 1.0f};      // at 0, 8, 16, 24, 32 warps
+            static const float r16[] = {0.0f, 0.43f, 0.86f, 1.09f, 1.185f};
+            const float *r = lpc == 16 ? r16 : r32;
+            const float x = std::min(32, std::max(0, warps)) / 8.0f;
+            const int i = std::min(3, (int)x);
+            return r[i] + (r[i + 1] - r[i]) * (x - i);
+        };
+        // One group of 32 lanes per chain unless asked otherwise: 16-lane groups retire ~12 % fewer
+        // instructions per proposal but two slabs per warp cost residency, and measured throughput is equal.
+        // CTA durations differ between schedules, so partial waves cost only ~5 %: take the full residency.
+        int best_ctas_spec = 0;
+        float best_score = 0.f;
+        if (p->algo == MCQ_ALGO_TABLE && (p->lanes_per_chain == 16 || p->lanes_per_chain == 32)) spec_lpc = p->lanes_per_chain;
+        best_ctas_spec = max_ctas(spec_lpc);
+        if (p->max_chains_per_sm > 0) best_ctas_spec = std::max(1, std::min(best_ctas_spec, p->max_chains_per_sm / (w * (32 / spec_lpc))));
+        best_score = rate(spec_lpc, best_ctas_spec * w);
+        if (best_ctas_spec == 0) return fail(MCQ_ENOMEM, "conflict-table slab does not fit in shared memory; lower warps_per_cta");
+        cpc = w * (32 / spec_lpc);
         block = w * 32;
         grid = (nc + cpc - 1) / cpc;
-        smem = (size_t)sl.cta_bytes + (size_t)cpc * sl.stride;
-        if (smem > smem_block) return fail(MCQ_ENOMEM, "conflict-table slab does not fit in shared memory; lower warps_per_cta");
-        if (p->max_chains_per_sm > 0) {
-            const int ctas = std::max(1, p->max_chains_per_sm / cpc);
-            size_t pad = std::min(smem_sm / ctas - 1024, smem_block) & ~(size_t)15;
-            smem = std::max(smem, pad);
+        smem = cta_smem(spec_lpc);
+        if (best_ctas_spec < max_ctas(spec_lpc)) {   // cap residency by padding the request (1 KB allocation granules)
+            size_t pad = (smem_sm / best_ctas_spec - 1024) / 1024 * 1024;
+            smem = std::max(smem, std::min(pad, smem_block));
         }
+        if (getenv("MCQ_DEBUG"))
+            fprintf(stderr, "[mcq] table kernel: lanes/chain %d, %d warps/CTA, %d CTAs/SM (max %d), grid %d, smem %zu B, score %.3f\n",
+                    spec_lpc, w, best_ctas_spec, max_ctas(spec_lpc), grid, smem, best_score);
     } else {   // cap residency (explicit limit, or balance the waves) by padding the shared-memory request
         int ctas = best_ctas;
         const int sms = ctx->prop.multiProcessorCount;
@@ -741,32 +782,35 @@ int mcq_run(mcq_ctx *ctx, const mcq_run_params *p) {
     if (hkind != MCQ_HIST_NONE && !direct) {
         const size_t bytes = (size_t)nc * chunk_pitch * esz;
         if (ctx->buf[B_HIST0].ensure(bytes)) return fail(MCQ_ENOMEM, "device allocation failed (history chunk)");
-        if (ns > chunk && ctx->buf[B_HIST1].ensure(bytes)) return fail(MCQ_ENOMEM, "device allocation failed (history chunk)");
     }
 
     // ---- the launches ----
-    std::vector<cudaEvent_t> ev;
-    cudaEvent_t buf_free[2] = {nullptr, nullptr}, chunk_done = nullptr;
-    if (want_hist && !direct) {
-        CUDA_TRY(cudaEventCreateWithFlags(&buf_free[0], cudaEventDisableTiming));
-        CUDA_TRY(cudaEventCreateWithFlags(&buf_free[1], cudaEventDisableTiming));
-        CUDA_TRY(cudaEventCreateWithFlags(&chunk_done, cudaEventDisableTiming));
+    // All CTAs of a launch take about the same time, so a launch that needs a fractional number of waves
+    // leaves SMs idle in its last one.  The chains are therefore split into two groups that advance on
+    // their own streams: while one group's launch drains, the other group's CTAs fill the free slots.
+    // Within a group everything is stream-ordered: kernel(chunk k) -> statistics / D2H of chunk k ->
+    // kernel(chunk k+1), which is also what lets one history buffer serve every chunk.
+    // (Measured: CTA durations vary enough between schedules that one stream loses only ~5 % to partial
+    // waves and two streams do not recover it, so one stream is the default; MCQ_STREAMS=2..4 enables the split.)
+    int n_sub = 1;
+    if (const char *e = getenv("MCQ_STREAMS")) n_sub = std::max(1, std::min(4, std::min(atoi(e), grid)));
+    cudaStream_t sub_stream[4];
+    for (int b = 0; b < n_sub; ++b) sub_stream[b] = n_sub == 1 ? s : ctx->sub_stream[b];
+    cudaEvent_t e_start, e_end, e_sub[4];
+    CUDA_TRY(cudaEventCreate(&e_start));
+    CUDA_TRY(cudaEventCreate(&e_end));
+    CUDA_TRY(cudaEventRecord(e_start, s));
+    for (int b = 0; b < n_sub && n_sub > 1; ++b) {
+        CUDA_TRY(cudaEventCreateWithFlags(&e_sub[b], cudaEventDisableTiming));
+        CUDA_TRY(cudaStreamWaitEvent(sub_stream[b], e_start, 0));
     }
-    int rc_loop = 0;
-    int ci = 0;
-    int t0 = 0;
-    do {
+    for (int t0 = 0, first_pass = 1; t0 < ns || first_pass; first_pass = 0) {
         const int t1 = std::min(ns, t0 + chunk);
         a.t_begin = t0; a.t_end = t1;
         a.hist_kind = hkind;
         if (hkind != MCQ_HIST_NONE) {
             if (direct) { a.hist = p->energy_history; a.hist_pitch = p->hist_pitch; a.h_origin = 0; }
-            else {
-                a.hist = ctx->buf[(ci & 1) ? B_HIST1 : B_HIST0].p;
-                a.hist_pitch = chunk_pitch;
-                a.h_origin = t0 == 0 ? 0 : (long long)t0 + 1;
-                if (want_hist && ci >= 2) CUDA_TRY(cudaStreamWaitEvent(s, buf_free[ci & 1], 0));
-            }
+            else { a.hist = ctx->buf[B_HIST0].p; a.hist_pitch = chunk_pitch; a.h_origin = t0 == 0 ? 0 : (long long)t0 + 1; }
         }
         a.bin_at_begin = 0;
         if (p->n_bins > 0) {
@@ -776,39 +820,46 @@ int mcq_run(mcq_ctx *ctx, const mcq_run_params *p) {
             if (t0 > 0) while (b + 1 < p->n_bins && p->bin_starts[b + 1] <= t0 - 1) ++b;
             a.bin_at_begin = b;
         }
-        cudaEvent_t e0, e1;
-        CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1));
-        ev.push_back(e0); ev.push_back(e1);
-        CUDA_TRY(cudaEventRecord(e0, s));
-        CUDA_TRY(use_spec ? launch_spec(a, replay, grid, block, smem, s) : launch_anneal(G, a, replay, grid, block, smem, s));
-        CUDA_TRY(cudaEventRecord(e1, s));
-        ++launches;
-        // first history column of this launch and how many columns it produced
+        // first history column of this chunk and how many columns it produces
         const long long h0 = t0 == 0 ? 0 : (long long)t0 + 1;
         const int n_cols = (int)((long long)t1 + 1 - h0);
-        if (want_stats && n_cols > 0) {
-            const void *hb = direct ? static_cast<const char *>(p->energy_history) + (size_t)h0 * esz : a.hist;
-            const long long hp = direct ? p->hist_pitch : chunk_pitch;
-            dim3 sg((n_cols + 127) / 128, std::max(1, std::min(64, nc / 256)));
-            if (hkind == MCQ_HIST_U16)
-                stats_kernel<uint16_t><<<sg, 128, 0, s>>>(static_cast<const uint16_t *>(hb), hp, n_cols, h0, nc, a.group, a.steps_done, d_sum_e, d_sum_e2, (long long)ns + 1);
-            else
-                stats_kernel<int><<<sg, 128, 0, s>>>(static_cast<const int *>(hb), hp, n_cols, h0, nc, a.group, a.steps_done, d_sum_e, d_sum_e2, (long long)ns + 1);
-            CUDA_TRY(cudaGetLastError());
+        for (int b = 0; b < n_sub; ++b) {
+            const int cta_lo = (int)((long long)grid * b / n_sub), cta_hi = (int)((long long)grid * (b + 1) / n_sub);
+            const int lo = cta_lo * cpc, hi = std::min(nc, cta_hi * cpc);
+            if (hi <= lo) continue;
+            cudaStream_t sb = sub_stream[b];
+            a.chain_begin = lo; a.n_chains = hi;
+            CUDA_TRY(use_spec ? launch_spec(spec_lpc, a, replay, cta_hi - cta_lo, block, smem, sb)
+                              : launch_anneal(G, a, replay, cta_hi - cta_lo, block, smem, sb));
             ++launches;
-        }
-        if (want_hist && !direct && n_cols > 0) {
-            CUDA_TRY(cudaEventRecord(chunk_done, s));
-            CUDA_TRY(cudaStreamWaitEvent(ctx->copy_stream, chunk_done, 0));
-            CUDA_TRY(cudaMemcpy2DAsync(static_cast<char *>(p->energy_history) + (size_t)h0 * esz, (size_t)p->hist_pitch * esz,
-                                       a.hist, (size_t)chunk_pitch * esz, (size_t)n_cols * esz, nc, cudaMemcpyDeviceToHost,
-                                       ctx->copy_stream));
-            CUDA_TRY(cudaEventRecord(buf_free[ci & 1], ctx->copy_stream));
+            if (want_stats && n_cols > 0) {
+                const char *hb = direct ? static_cast<const char *>(p->energy_history) + (size_t)h0 * esz : static_cast<const char *>(a.hist);
+                const long long hp = direct ? p->hist_pitch : chunk_pitch;
+                hb += (size_t)lo * hp * esz;
+                const int n = hi - lo;
+                const int *grp = a.group ? a.group + lo : nullptr;
+                dim3 sg((n_cols + 127) / 128, std::max(1, std::min(64, n / 256)));
+                if (hkind == MCQ_HIST_U16)
+                    stats_kernel<uint16_t><<<sg, 128, 0, sb>>>(reinterpret_cast<const uint16_t *>(hb), hp, n_cols, h0, n, grp, a.steps_done + lo, d_sum_e, d_sum_e2, (long long)ns + 1);
+                else
+                    stats_kernel<int><<<sg, 128, 0, sb>>>(reinterpret_cast<const int *>(hb), hp, n_cols, h0, n, grp, a.steps_done + lo, d_sum_e, d_sum_e2, (long long)ns + 1);
+                CUDA_TRY(cudaGetLastError());
+                ++launches;
+            }
+            if (want_hist && !direct && n_cols > 0) {
+                CUDA_TRY(cudaMemcpy2DAsync(static_cast<char *>(p->energy_history) + ((size_t)lo * p->hist_pitch + (size_t)h0) * esz,
+                                           (size_t)p->hist_pitch * esz, static_cast<const char *>(a.hist) + (size_t)lo * chunk_pitch * esz,
+                                           (size_t)chunk_pitch * esz, (size_t)n_cols * esz, hi - lo, cudaMemcpyDeviceToHost, sb));
+            }
         }
         t0 = t1;
-        ++ci;
-    } while (t0 < ns);
-    (void)rc_loop;
+    }
+    a.chain_begin = 0; a.n_chains = nc;
+    for (int b = 0; b < n_sub && n_sub > 1; ++b) {
+        CUDA_TRY(cudaEventRecord(e_sub[b], sub_stream[b]));
+        CUDA_TRY(cudaStreamWaitEvent(s, e_sub[b], 0));
+    }
+    CUDA_TRY(cudaEventRecord(e_end, s));
 
     // ---- outputs ----
     if (int rc = copy_out(p->initial_energy, a.init_e, (size_t)nc * 4, mem, s)) return rc;
@@ -831,15 +882,10 @@ int mcq_run(mcq_ctx *ctx, const mcq_run_params *p) {
     uint32_t h_err = 0;
     if (replay) CUDA_TRY(cudaMemcpyAsync(&h_err, a.replay_err, 4, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
-    if (want_hist && !direct) CUDA_TRY(cudaStreamSynchronize(ctx->copy_stream));
     float ms_total = 0.f;
-    for (size_t i = 0; i + 1 < ev.size(); i += 2) {
-        float ms = 0.f;
-        CUDA_TRY(cudaEventElapsedTime(&ms, ev[i], ev[i + 1]));
-        ms_total += ms;
-    }
-    for (auto e : ev) cudaEventDestroy(e);
-    if (buf_free[0]) { cudaEventDestroy(buf_free[0]); cudaEventDestroy(buf_free[1]); cudaEventDestroy(chunk_done); }
+    CUDA_TRY(cudaEventElapsedTime(&ms_total, e_start, e_end));   // device span of all launches of this call
+    cudaEventDestroy(e_start); cudaEventDestroy(e_end);
+    for (int b = 0; b < n_sub && n_sub > 1; ++b) cudaEventDestroy(e_sub[b]);
     if (p->kernel_ms) *p->kernel_ms = ms_total;
     if (p->gpu_launches) *p->gpu_launches = launches;
     if (replay && h_err) return fail(MCQ_EREPLAY, "replayed stream contained an illegal proposal (occupied cell, same height or out of range)");

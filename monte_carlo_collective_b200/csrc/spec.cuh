@@ -173,14 +173,18 @@ __device__ __forceinline__ float ex2_approx(float x) {
     return y;
 }
 
-// lane-0 scalars kept in the slab instead of registers (byte offsets from sl.off_rec)
-enum RecSlot { R_BEST_STEP = 0, R_BIN_MARK = 4, R_BIN = 8, R_NEAR = 12 };
-
-template <bool FULL, bool REPLAY, bool EARLY, int NR>
+// One lane group of LPC lanes (32 or 16) owns a chain; a warp carries 32/LPC chains.  Narrower
+// groups waste fewer evaluated proposals per round (at 3 % acceptance a 16-lane group commits
+// 12.9 of 16, a 32-lane group 20.7 of 32); committed moves are applied by the whole warp, one
+// chain after the other, so the table update keeps 32 lanes busy either way.
+template <bool FULL, bool REPLAY, bool EARLY, int NR, int LPC>
 __global__ void __launch_bounds__(128, MCQ_SPEC_MINB) spec_kernel(const __grid_constant__ KArgs a) {
     constexpr unsigned FULLMASK = 0xffffffffu;
     constexpr int NF = FULL ? NFAM : NFAM - 1;
+    constexpr int CPW = 32 / LPC;   // chains per warp
+    constexpr unsigned LMASK = LPC == 32 ? 0xffffffffu : ((1u << LPC) - 1u);
     const int lane = threadIdx.x & 31;
+    const int sub = lane & (LPC - 1), half = lane / LPC;
     const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem);
     const int N = a.N;
 
@@ -189,87 +193,94 @@ __global__ void __launch_bounds__(128, MCQ_SPEC_MINB) spec_kernel(const __grid_c
         for (int w = threadIdx.x; w < a.sl.cta_bytes / 4; w += blockDim.x) SM32(4 * w) = __ldg(a.geo + w);
         __syncthreads();
     }
-    const int chain = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (chain >= a.n_chains) return;
+    const int slab0 = (int)(threadIdx.x >> 5) * CPW;                      // first slab of this warp
+    const int chain0 = a.chain_begin + (blockIdx.x * (blockDim.x >> 5)) * CPW + slab0;   // first chain of this warp
+    if (chain0 >= a.n_chains) return;
+    const int chain = chain0 + half;
+    const bool live = chain < a.n_chains;
+    const int chain_c = live ? chain : chain0;                            // for pointer set-up only
 
-    const int sT = a.sl.cta_bytes + (int)(threadIdx.x >> 5) * a.sl.stride;   // table T[N^3 + 1]
+    const int sT = a.sl.cta_bytes + (slab0 + half) * a.sl.stride;   // table T[N^3 + 1]
     const int sP = sT + a.sl.off_state;   // board: heights u8; full_3d: u32 per queen = cell id | wide id << 16
     const int sO = sT + a.sl.off_occ;     // full_3d: occupancy bits
-    const int sR = sT + a.sl.off_rec;     // lane-0 record
     const int sW = a.sl.off_wide;
     const int L = a.sl.nbr_len, rounds = a.sl.rounds;
     const uint32_t wide_bias = (uint32_t)((N - 1) * ((2 * N - 1) * (2 * N - 1) + (2 * N - 1) + 1));
 
-    // ---- build the slab from the external state ----
-    for (int w = lane; w < a.sl.stride / 4; w += 32) SM32(sT + 4 * w) = 0u;
-    __syncwarp();
-    const uint8_t *ext = a.state + (size_t)chain * a.state_bytes;
-    for (int qi = lane; qi < a.Q; qi += 32) {
-        if (FULL) {
-            const int cid = ((int)ext[3 * qi] * N + (int)ext[3 * qi + 1]) * N + (int)ext[3 * qi + 2];
-            SM32(sP + 4 * qi) = (uint32_t)cid | ((uint32_t)SM16(sW + 2 * cid) << 16);
-            sm_red_or(sbase + (uint32_t)(sO + 4 * (cid >> 5)), 1u << (cid & 31));
-        } else {
-            SM8(sP + qi) = ext[qi];
-        }
-    }
-    __syncwarp();
-    for (int qi = 0; qi < a.Q; ++qi) {
-        const int c = FULL ? (int)(SM32(sP + 4 * qi) & 0xffffu) : qi * N + (int)SM8(sP + qi);
-        table_lines_add<NR>(sbase + (uint32_t)sT, a.nbr, (uint32_t)(c * L + lane), rounds, 1);
-        if (lane == 0) SM8(sT + c) = (unsigned char)(SM8(sT + c) + NF);
+    // ---- build the slabs from the external states: one chain at a time, all 32 lanes ----
+    int E = 0;
+    for (int h = 0; h < CPW; ++h) {
+        const int bT = a.sl.cta_bytes + (slab0 + h) * a.sl.stride, bP = bT + a.sl.off_state, bO = bT + a.sl.off_occ;
+        for (int w = lane; w < a.sl.stride / 4; w += 32) SM32(bT + 4 * w) = 0u;
         __syncwarp();
-    }
-    int E;
-    {
+        if (chain0 + h >= a.n_chains) continue;   // no chain: the slab stays zero (harmless to evaluate)
+        const uint8_t *ext = a.state + (size_t)(chain0 + h) * a.state_bytes;
+        for (int qi = lane; qi < a.Q; qi += 32) {
+            if (FULL) {
+                const int cid = ((int)ext[3 * qi] * N + (int)ext[3 * qi + 1]) * N + (int)ext[3 * qi + 2];
+                SM32(bP + 4 * qi) = (uint32_t)cid | ((uint32_t)SM16(sW + 2 * cid) << 16);
+                sm_red_or(sbase + (uint32_t)(bO + 4 * (cid >> 5)), 1u << (cid & 31));
+            } else {
+                SM8(bP + qi) = ext[qi];
+            }
+        }
+        __syncwarp();
+        for (int qi = 0; qi < a.Q; ++qi) {
+            const int c = FULL ? (int)(SM32(bP + 4 * qi) & 0xffffu) : qi * N + (int)SM8(bP + qi);
+            table_lines_add<NR>(sbase + (uint32_t)bT, a.nbr, (uint32_t)(c * L + lane), rounds, 1);
+            if (lane == 0) SM8(bT + c) = (unsigned char)(SM8(bT + c) + NF);
+            __syncwarp();
+        }
         int e = 0;
         for (int qi = lane; qi < a.Q; qi += 32) {
-            const int c = FULL ? (int)(SM32(sP + 4 * qi) & 0xffffu) : qi * N + (int)SM8(sP + qi);
-            e += (int)SM8(sT + c) - NF;
+            const int c = FULL ? (int)(SM32(bP + 4 * qi) & 0xffffu) : qi * N + (int)SM8(bP + qi);
+            e += (int)SM8(bT + c) - NF;
         }
-        E = __reduce_add_sync(FULLMASK, e) >> 1;   // every attacking pair was counted from both ends
+        e = __reduce_add_sync(FULLMASK, e) >> 1;   // every attacking pair was counted from both ends
+        if (half == h) E = e;
     }
 
-    // ---- persistent record ----
-    int best = E, stale = 0, n_acc = 0;
+    // ---- persistent record (every lane of a group holds its chain's scalars) ----
+    int best = E, stale = 0, n_acc = 0, best_step = 0, bin_mark = 0;
     int done = a.t_end;
-    int t = a.t_begin;
-    if (a.t_begin == 0) {
-        if (lane == 0) {
-            if (a.init_e) a.init_e[chain] = E;
-            if (a.hist_kind == 1) reinterpret_cast<uint16_t *>(a.hist)[(size_t)chain * a.hist_pitch] = (uint16_t)E;
-            else if (a.hist_kind == 2) reinterpret_cast<int *>(a.hist)[(size_t)chain * a.hist_pitch] = E;
+    int t = live ? a.t_begin : a.t_end;
+    if (live) {
+        if (a.t_begin == 0) {
+            if (sub == 0) {
+                if (a.init_e) a.init_e[chain] = E;
+                if (a.hist_kind == 1) reinterpret_cast<uint16_t *>(a.hist)[(size_t)chain * a.hist_pitch] = (uint16_t)E;
+                else if (a.hist_kind == 2) reinterpret_cast<int *>(a.hist)[(size_t)chain * a.hist_pitch] = E;
+            }
+        } else {
+            best = a.best_e[chain];
+            stale = a.stale[chain];
+            n_acc = a.n_acc[chain];
+            best_step = a.best_step[chain];
+            bin_mark = a.bin_mark[chain];
+            const int sd = a.steps_done[chain];
+            if (sd < a.t_begin) { done = sd; t = a.t_end; }   // stopped in an earlier launch
         }
-    } else {
-        best = a.best_e[chain];
-        stale = a.stale[chain];
-        n_acc = a.n_acc[chain];
-        if (lane == 0) {
-            SM32(sR + R_BEST_STEP) = (uint32_t)a.best_step[chain];
-            SM32(sR + R_BIN_MARK) = (uint32_t)a.bin_mark[chain];
-        }
-        const int sd = a.steps_done[chain];
-        if (sd < a.t_begin) { done = sd; t = a.t_end; }   // stopped in an earlier launch
     }
-    if (lane == 0) SM32(sR + R_BIN) = (uint32_t)a.bin_at_begin;
-    __syncwarp();
-    const unsigned long long sd64 = a.seeds ? a.seeds[chain] : 0ull;
+    const unsigned long long sd64 = a.seeds ? a.seeds[chain_c] : 0ull;
     const uint32_t key0 = (uint32_t)sd64, key1 = (uint32_t)(sd64 >> 32);
-    const int grp = a.group ? a.group[chain] : 0;
+    const int grp = a.group ? a.group[chain_c] : 0;
     const float *beta_row = REPLAY ? nullptr : a.beta_c + (size_t)grp * a.n_steps;
     const double *beta64_row = REPLAY ? a.beta64 + (size_t)grp * a.n_steps : nullptr;
-    const uint32_t *mv_row = REPLAY ? a.rmoves + (size_t)chain * a.n_steps : nullptr;
-    const double *un_row = REPLAY ? a.runif + (size_t)chain * a.n_steps : nullptr;
-    int next_edge = a.n_bins > 0 ? a.bin_starts[a.bin_at_begin + 1] : 0x7fffffff;
+    const uint32_t *mv_row = REPLAY ? a.rmoves + (size_t)chain_c * a.n_steps : nullptr;
+    const double *un_row = REPLAY ? a.runif + (size_t)chain_c * a.n_steps : nullptr;
+    int bin = a.bin_at_begin;
+    int next_edge = a.n_bins > 0 ? a.bin_starts[bin + 1] : 0x7fffffff;
+    [[maybe_unused]] uint32_t near = 0u;
     // history row, addressed by history index h = step + 1 (h_origin = index held by column 0)
     unsigned char *hrow = static_cast<unsigned char *>(a.hist) +
-                          ((long long)chain * a.hist_pitch - a.h_origin) * (a.hist_kind == 1 ? 2 : 4);
-    uint32_t *abits_row = a.abits ? a.abits + (size_t)chain * a.abits_pitch : nullptr;
+                          ((long long)chain_c * a.hist_pitch - a.h_origin) * (a.hist_kind == 1 ? 2 : 4);
+    uint32_t *abits_row = a.abits ? a.abits + (size_t)chain_c * a.abits_pitch : nullptr;
 
-    while (t < a.t_end) {
-        const int rem = a.t_end - t;                       // >= 1
-        const bool valid = lane < rem;
-        const int s = t + (valid ? lane : rem - 1);        // lanes past the end redo the last step, masked below
+    while (CPW == 1 ? t < a.t_end : __any_sync(FULLMASK, t < a.t_end)) {
+        const bool active = CPW == 1 || t < a.t_end;
+        const int rem = a.t_end - t;                        // >= 1 while active
+        const bool valid = active && sub < rem;
+        const int s = min(t + sub, a.t_end - 1);            // lanes past the end redo the last step, masked below
 
         // ---------------- this lane's proposal: step s against the current state ----------------
         uint32_t c0, c1, aux;   // old cell, new cell, and what the commit needs besides them
@@ -349,125 +360,137 @@ __global__ void __launch_bounds__(128, MCQ_SPEC_MINB) spec_kernel(const __grid_c
         }
         accept = accept && valid;
 
-        // ---------------- commit the first accepted proposal ----------------
-        const unsigned acc_mask = __ballot_sync(FULLMASK, accept);
+        // ---------------- each group commits its first accepted proposal ----------------
+        const unsigned acc_mask = (__ballot_sync(FULLMASK, accept) >> (half * LPC)) & LMASK;
         int first = acc_mask ? __ffs(acc_mask) - 1 : -1;
-        int adv = first >= 0 ? first + 1 : min(32, rem);   // steps consumed by this round
-        int adv_h = adv;                                   // steps whose energy is appended to the history
+        int adv = !active ? 0 : first >= 0 ? first + 1 : min(LPC, rem);   // steps consumed by this round
+        int adv_h = adv;                                                  // steps whose energy is appended to the history
         bool stop = false;
-        int E_new = E;
-        if (first >= 0) E_new = E + __shfl_sync(FULLMASK, dE, first);
+        const int src = half * LPC + max(first, 0);                       // the group's winning lane
+        const int wdE = __shfl_sync(FULLMASK, dE, src);
+        int E_new = first >= 0 ? E + wdE : E;
         bool improved = E_new < best;
         if constexpr (EARLY) {
             // experiments.py:343-353: the counter resets on a strict improvement only, and the
             // break happens before the history append of the stopping step
-            const int e_stop = max(a.patience - stale - 1, 0);   // rejected step at which patience runs out
-            if (first < 0 || first > e_stop) {
-                if (e_stop < min(32, rem)) { stop = true; first = -1; adv = e_stop + 1; adv_h = e_stop; stale += e_stop + 1; E_new = E; improved = false; }
-                else stale += adv;
-            } else {
-                stale = improved ? 0 : stale + first + 1;
-                if (stale >= a.patience) { stop = true; adv_h = first; }
+            if (active) {
+                const int e_stop = max(a.patience - stale - 1, 0);   // rejected step at which patience runs out
+                if (first < 0 || first > e_stop) {
+                    if (e_stop < min(LPC, rem)) { stop = true; first = -1; adv = e_stop + 1; adv_h = e_stop; stale += e_stop + 1; E_new = E; improved = false; }
+                    else stale += adv;
+                } else {
+                    stale = improved ? 0 : stale + first + 1;
+                    if (stale >= a.patience) { stop = true; adv_h = first; }
+                }
             }
         }
         if constexpr (REPLAY) {
             const unsigned committed = adv >= 32 ? FULLMASK : ((1u << adv) - 1u);
-            const unsigned nearm = __ballot_sync(FULLMASK, near_flag && valid) & committed;
-            const unsigned badm = __ballot_sync(FULLMASK, bad && valid) & committed;
-            if (lane == 0) {
-                SM32(sR + R_NEAR) += (uint32_t)__popc(nearm);
-                if (badm) atomicAdd(a.replay_err, (unsigned)__popc(badm));
-            }
+            const unsigned nearm = (__ballot_sync(FULLMASK, near_flag && valid) >> (half * LPC)) & LMASK & committed;
+            const unsigned badm = (__ballot_sync(FULLMASK, bad && valid) >> (half * LPC)) & LMASK & committed;
+            near += (uint32_t)__popc(nearm);
+            if (badm && sub == 0) atomicAdd(a.replay_err, (unsigned)__popc(badm));
         }
         // history: steps t .. t+adv_h-1; all but an accepted last one keep the old energy
-        if (lane < adv_h && a.hist_kind) {
-            const int v = (lane == first) ? E_new : E;
+        if (sub < adv_h && a.hist_kind) {
+            const int v = (sub == first) ? E_new : E;
             if (a.hist_kind == 1) reinterpret_cast<uint16_t *>(hrow)[s + 1] = (uint16_t)v;
             else reinterpret_cast<int *>(hrow)[s + 1] = v;
         }
         // acceptance bins: close every bin that ends at or before the last consumed step
-        if (t + adv - 1 >= next_edge) {
-            int bin = (int)SM32(sR + R_BIN);
-            __syncwarp();
+        if (active) {
             while (t + adv - 1 >= next_edge) {
-                if (lane == 0) {
-                    if (a.acc_hist) a.acc_hist[(size_t)chain * a.n_bins + bin] = (uint32_t)n_acc - SM32(sR + R_BIN_MARK);
-                    SM32(sR + R_BIN_MARK) = (uint32_t)n_acc;
-                }
+                if (sub == 0 && a.acc_hist) a.acc_hist[(size_t)chain * a.n_bins + bin] = (uint32_t)(n_acc - bin_mark);
+                bin_mark = n_acc;
                 ++bin;
                 next_edge = a.bin_starts[bin + 1];
             }
-            if (lane == 0) SM32(sR + R_BIN) = (uint32_t)bin;
-            __syncwarp();
         }
-        if (first >= 0) {
-            const uint32_t wc0 = __shfl_sync(FULLMASK, c0, first);
-            const uint32_t wc1 = __shfl_sync(FULLMASK, c1, first);
-            const uint32_t waux = __shfl_sync(FULLMASK, aux, first);
-            table_lines_add<NR>(sbase + (uint32_t)sT, a.nbr, wc0 * (uint32_t)L + (uint32_t)lane, rounds, -1);
-            if (lane == 0) SM8(sT + wc0) = (unsigned char)(SM8(sT + wc0) - NF);
+        // ---------------- apply the committed moves: whole warp, one chain after the other ----------------
+        const bool has = first >= 0;
+        const uint32_t wc0 = __shfl_sync(FULLMASK, c0, src), wc1 = __shfl_sync(FULLMASK, c1, src);
+        const uint32_t waux = __shfl_sync(FULLMASK, aux, src);
+        // one bit (the group's lane 0) per committing chain; a single group needs no vote
+        unsigned upd = CPW == 1 ? (unsigned)has : __ballot_sync(FULLMASK, has && sub == 0);
+        while (upd) {
+            const int hl = CPW == 1 ? 0 : __ffs(upd) - 1;
+            upd &= upd - 1;
+            uint32_t bc0 = wc0, bc1 = wc1, baux = waux;
+            int bT = sT;
+            if constexpr (CPW > 1) {
+                bc0 = __shfl_sync(FULLMASK, wc0, hl); bc1 = __shfl_sync(FULLMASK, wc1, hl); baux = __shfl_sync(FULLMASK, waux, hl);
+                bT = a.sl.cta_bytes + (slab0 + hl / LPC) * a.sl.stride;
+            }
+            table_lines_add<NR>(sbase + (uint32_t)bT, a.nbr, bc0 * (uint32_t)L + (uint32_t)lane, rounds, -1);
+            if (lane == 0) SM8(bT + bc0) = (unsigned char)(SM8(bT + bc0) - NF);
             __syncwarp();
-            table_lines_add<NR>(sbase + (uint32_t)sT, a.nbr, wc1 * (uint32_t)L + (uint32_t)lane, rounds, +1);
-            const int ta = t + first;
+            table_lines_add<NR>(sbase + (uint32_t)bT, a.nbr, bc1 * (uint32_t)L + (uint32_t)lane, rounds, +1);
             if (lane == 0) {
-                SM8(sT + wc1) = (unsigned char)(SM8(sT + wc1) + NF);
+                SM8(bT + bc1) = (unsigned char)(SM8(bT + bc1) + NF);
+                const int bP = bT + a.sl.off_state;
                 if (FULL) {
-                    SM32(sO + 4 * (wc0 >> 5)) &= ~(1u << (wc0 & 31));
-                    SM32(sO + 4 * (wc1 >> 5)) |= 1u << (wc1 & 31);
-                    SM32(sP + 4 * (waux & 0xffffu)) = wc1 | (waux & 0xffff0000u);
+                    const int bO = bT + a.sl.off_occ;
+                    SM32(bO + 4 * (bc0 >> 5)) &= ~(1u << (bc0 & 31));
+                    SM32(bO + 4 * (bc1 >> 5)) |= 1u << (bc1 & 31);
+                    SM32(bP + 4 * (baux & 0xffffu)) = bc1 | (baux & 0xffff0000u);
                 } else {
-                    SM8(sP + (waux & 0xffffu)) = (unsigned char)(waux >> 16);
+                    SM8(bP + (baux & 0xffffu)) = (unsigned char)(baux >> 16);
                 }
-                if (abits_row) atomicOr(abits_row + (ta >> 5), 1u << (ta & 31));
-                if (improved && !stop) SM32(sR + R_BEST_STEP) = (uint32_t)(ta + 1);
             }
             __syncwarp();
+        }
+        if (has) {
+            const int ta = t + first;
             E = E_new;
             ++n_acc;
+            if (sub == 0 && abits_row) atomicOr(abits_row + (ta >> 5), 1u << (ta & 31));
             if (improved) {
                 // snapshot: the state at the first visit of the minimum (strict <, :252 / :340)
                 best = E;
+                if (!stop) best_step = ta + 1;
                 uint8_t *bs = a.best_state + (size_t)chain * a.state_bytes;
                 if (FULL) {
-                    for (int qi = lane; qi < a.Q; qi += 32) {
+                    for (int qi = sub; qi < a.Q; qi += LPC) {
                         const int c = (int)(SM32(sP + 4 * qi) & 0xffffu);
                         bs[3 * qi] = (uint8_t)(c / (N * N)); bs[3 * qi + 1] = (uint8_t)((c / N) % N); bs[3 * qi + 2] = (uint8_t)(c % N);
                     }
                 } else {
-                    for (int c = lane; c < a.Q; c += 32) bs[c] = SM8(sP + c);
+                    for (int c = sub; c < a.Q; c += LPC) bs[c] = SM8(sP + c);
                 }
             }
         }
         if (stop) {
             done = t + adv - 1;
-            if (lane == 0 && a.acc_hist) a.acc_hist[(size_t)chain * a.n_bins + SM32(sR + R_BIN)] = (uint32_t)n_acc - SM32(sR + R_BIN_MARK);
-            break;
+            if (sub == 0 && a.acc_hist) a.acc_hist[(size_t)chain * a.n_bins + bin] = (uint32_t)(n_acc - bin_mark);
+            t = a.t_end;   // this chain is finished; the other groups of the warp go on
+        } else {
+            t += adv;
         }
-        t += adv;
     }
 
     // ---------------- write the record back ----------------
     __syncwarp();
-    if (lane == 0) {
+    if (!live) return;
+    if (sub == 0) {
         if (a.t_end == a.n_steps && a.n_bins > 0 && a.acc_hist && done == a.t_end)
-            a.acc_hist[(size_t)chain * a.n_bins + SM32(sR + R_BIN)] = (uint32_t)n_acc - SM32(sR + R_BIN_MARK);
+            a.acc_hist[(size_t)chain * a.n_bins + bin] = (uint32_t)(n_acc - bin_mark);
         a.cur_e[chain] = E;
         a.best_e[chain] = best;
-        a.best_step[chain] = (int)SM32(sR + R_BEST_STEP);
+        a.best_step[chain] = best_step;
         a.n_acc[chain] = n_acc;
         a.stale[chain] = stale;
-        a.bin_mark[chain] = (int)SM32(sR + R_BIN_MARK);
+        a.bin_mark[chain] = bin_mark;
         a.steps_done[chain] = done;
-        if (REPLAY && a.near_cnt) a.near_cnt[chain] += SM32(sR + R_NEAR);
+        if (REPLAY && a.near_cnt) a.near_cnt[chain] += near;
     }
     uint8_t *out = a.state + (size_t)chain * a.state_bytes;
     if (FULL) {
-        for (int qi = lane; qi < a.Q; qi += 32) {
+        for (int qi = sub; qi < a.Q; qi += LPC) {
             const int c = (int)(SM32(sP + 4 * qi) & 0xffffu);
             out[3 * qi] = (uint8_t)(c / (N * N)); out[3 * qi + 1] = (uint8_t)((c / N) % N); out[3 * qi + 2] = (uint8_t)(c % N);
         }
     } else {
-        for (int c = lane; c < a.Q; c += 32) out[c] = SM8(sP + c);
+        for (int c = sub; c < a.Q; c += LPC) out[c] = SM8(sP + c);
     }
 }
 

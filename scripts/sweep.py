@@ -51,9 +51,29 @@ if which == "base":
         for n in (8, 15, 20):
             run("N", mode, n, 8192, 10000)
     run("N", "board", 64, 1184, 2000)
+elif which == "c2geo":
+    run("c2", "full_3d", 12, 20480, 200000, algo="table")
+    for lanes, m in ((32, 32), (32, 28), (16, 64), (16, 48), (16, 56)):
+        run("c2", "full_3d", 12, 20480, 200000, algo="table", lanes_per_chain=lanes, max_chains_per_sm=m)
+elif which == "auto":
+    run("auto", "full_3d", 12, 20480, 200000, algo="table")
+    run("auto", "board", 12, 20480, 100000, algo="table")
+    run("auto", "full_3d", 12, 4096, 100000, algo="table")
+    run("auto", "full_3d", 12, 1000, 100000, algo="table")
+    run("auto", "full_3d", 12, 65536, 50000, algo="table")
+    run("auto", "full_3d", 8, 20480, 100000, algo="table")
+    run("auto", "board", 15, 8192, 50000, algo="table")
+    run("auto", "board", 20, 8192, 20000, algo="table")
 elif which == "quick":
-    run("q", "full_3d", 12, 20480, 200000, algo="table")
-    run("q", "board", 12, 20480, 100000, algo="table")
+    for lanes in (32, 16):
+        run("q", "full_3d", 12, 20480, 200000, algo="table", lanes_per_chain=lanes)
+        run("q", "board", 12, 20480, 100000, algo="table", lanes_per_chain=lanes)
+elif which == "occ2":
+    for lanes in (32, 16):
+        cpw = 32 // lanes
+        for ctas in (4, 5, 6, 7, 8):
+            chains = 148 * ctas * 4 * cpw
+            run("occ2", "full_3d", 12, chains, 100000, algo="table", lanes_per_chain=lanes, max_chains_per_sm=ctas * 4 * cpw)
 elif which == "table":
     for mode in ("full_3d", "board"):
         for w in (1, 2, 4):
@@ -68,3 +88,9 @@ elif which == "occ":
     for G in (4, 8, 16):
         for m in (8, 16, 24, 32, 40, 48):
             run("occ", "full_3d", 12, 148 * m, 20000, lanes_per_chain=G, max_chains_per_sm=m)
+
+if which == "tail":
+    for st in ("1", "2"):
+        os.environ["MCQ_STREAMS"] = st
+        for nc in (4736 * 4, 20480, 4736 * 5, 4736 * 4 + 148 * 4):
+            run("tail" + st, "full_3d", 12, nc, 100000, algo="table", lanes_per_chain=32)

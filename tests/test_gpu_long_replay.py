@@ -45,11 +45,12 @@ def test_long_replay_matches_c_oracle(engine, case):
     table_ok = 13 * n <= 255 if mode == "full_3d" else 12 * n <= 255
     variants = [dict(algo="lines", lanes_per_chain=8), dict(algo="lines", lanes_per_chain=32)]
     if table_ok:
-        variants += [dict(algo="table"), dict(algo="table", chunk_steps=2048)]
+        variants += [dict(algo="table"), dict(algo="table", chunk_steps=2048), dict(algo="table", lanes_per_chain=32),
+                     dict(algo="table", lanes_per_chain=16)]
     if n <= 16:
         variants.append(dict(algo="lines", lanes_per_chain=4, chunk_steps=4096))
     for kw in variants:
-        lanes = kw.get("lanes_per_chain")
+        lanes = kw.get("lanes_per_chain") if kw.get("algo") == "lines" else None
         if lanes:      # a warp carries 32/lanes chains: skip widths whose slabs do not fit one CTA
             from monte_carlo_collective_b200 import _lib
             slab = _lib.load().mcq_chain_smem_bytes(1 if mode == "full_3d" else 0, n, n * n, lanes)
@@ -77,7 +78,8 @@ def test_early_stop_replay_matches_c_oracle(engine, patience):
     betas = np.full(ns, 3.5)
     free = c_oracle.generate("board", n, st, betas, seed=99)
     want = c_oracle.replay("board", n, st, free["moves"], free["uniforms"], betas, patience=patience)
-    for kw in (dict(algo="table"), dict(algo="lines"), dict(algo="table", chunk_steps=32), dict(algo="lines", chunk_steps=96)):
+    for kw in (dict(algo="table"), dict(algo="lines"), dict(algo="table", chunk_steps=32), dict(algo="lines", chunk_steps=96),
+               dict(algo="table", lanes_per_chain=32), dict(algo="table", lanes_per_chain=16)):
         r = engine.run("board", n, ns, np.array([1], dtype=np.uint64), betas, init_states=st[None].astype(np.uint8),
                        history="full", hist_dtype=np.int32, accept_bits=True, early_stop_patience=patience,
                        replay={"moves": free["moves"][None], "uniforms": free["uniforms"][None]}, **kw)

@@ -58,6 +58,8 @@ def test_same_seed_same_chain_any_layout(engine, mode):
     for kw in (dict(lanes_per_chain=4), dict(lanes_per_chain=16), dict(lanes_per_chain=32, warps_per_cta=1),
                dict(chunk_steps=320), dict(warps_per_cta=3), dict(max_chains_per_sm=8),
                dict(algo="table", warps_per_cta=1), dict(algo="table", chunk_steps=96, warps_per_cta=2),
+               dict(algo="table", lanes_per_chain=32), dict(algo="table", lanes_per_chain=16, warps_per_cta=3),
+               dict(algo="table", lanes_per_chain=32, chunk_steps=64), dict(algo="table", lanes_per_chain=16, chunk_steps=64),
                dict(algo="lines", chunk_steps=320, warps_per_cta=3)):
         r = engine.run(mode, n, ns, seeds, betas, history="full", accept_bits=True, **kw)
         assert (r.energy_history == base.energy_history).all(), kw
@@ -138,7 +140,8 @@ def test_early_stop_board(engine):
     free = engine.run("board", n, ns, seeds, betas, history="full", accept_bits=True)
     stop = engine.run("board", n, ns, seeds, betas, history="full", accept_bits=True, early_stop_patience=300, n_bins=100)
     assert (stop.steps_done < ns).any()
-    for kw in (dict(algo="lines"), dict(algo="lines", lanes_per_chain=32, chunk_steps=128), dict(algo="table", chunk_steps=64)):
+    for kw in (dict(algo="lines"), dict(algo="lines", lanes_per_chain=32, chunk_steps=128), dict(algo="table", chunk_steps=64),
+               dict(algo="table", lanes_per_chain=32), dict(algo="table", lanes_per_chain=16, chunk_steps=160)):
         other = engine.run("board", n, ns, seeds, betas, history="full", accept_bits=True, early_stop_patience=300,
                            n_bins=100, **kw)
         for name in ("steps_done", "final_energy", "best_energy", "steps_to_best", "n_accepted", "final_state",
@@ -149,6 +152,11 @@ def test_early_stop_board(engine):
             assert (other.energy_history[c, : d + 1] == stop.energy_history[c, : d + 1]).all(), kw
     for pat in (0, 1, 2, 33):
         a = engine.run("board", n, 400, seeds, betas[:400], history="full", accept_bits=True, early_stop_patience=pat, algo="table")
+        for lanes in (16, 32):
+            c = engine.run("board", n, 400, seeds[:33], betas[:400], history="full", accept_bits=True, early_stop_patience=pat,
+                           algo="table", lanes_per_chain=lanes)
+            for name in ("steps_done", "final_energy", "best_energy", "steps_to_best", "n_accepted", "final_state", "best_state", "accept_bits"):
+                assert (getattr(c, name) == getattr(a, name)[:33]).all(), (pat, lanes, name)
         b = engine.run("board", n, 400, seeds, betas[:400], history="full", accept_bits=True, early_stop_patience=pat, algo="lines")
         for name in ("steps_done", "final_energy", "best_energy", "steps_to_best", "n_accepted", "final_state", "best_state", "accept_bits"):
             assert (getattr(a, name) == getattr(b, name)).all(), (pat, name)

@@ -53,10 +53,10 @@ def test_replay_batch_and_chunked_launches(engine):
         g = np.load(path)
         mode, n, ns = str(g["mode"]), int(g["n"]), int(g["n_steps"])
         reps = 5
-        for algo in ("table", "lines"):
+        for algo, lanes in (("table", 16), ("table", 32), ("lines", 8)):
             r = engine.run(mode, n, ns, np.arange(reps, dtype=np.uint64), g["betas"],
                            init_states=np.repeat(g["init_state"][None], reps, 0).astype(np.uint8),
-                           history="full", accept_bits=True, chunk_steps=352, algo=algo,
+                           history="full", accept_bits=True, chunk_steps=352, algo=algo, lanes_per_chain=lanes,
                            replay={"moves": np.repeat(g["moves"][None], reps, 0),
                                    "uniforms": np.repeat(g["uniforms"][None], reps, 0)})
             assert r.gpu_launches >= ns // 352
