@@ -52,8 +52,10 @@ SCHEDULES = [
 I_ALG = {"full_3d": 48.0, "board": 40.0}
 ISSUE_PER_CLK_PER_SM = 4
 # ncu measurements of the dominant kernel on this workload (profiles/README.md says which capture)
-AS_BUILT = {"source": "profiles/r1_spec_kernel_raw.txt", "warp_inst_per_proposal": 18.7, "issue_active_pct": 72.8,
-            "warps_active_per_scheduler": 7.0, "registers_per_thread": 64, "smem_wavefronts_per_proposal": 3.8}
+AS_BUILT = {"source": "profiles/r1_spec_kernel_raw.txt (ncu --set full, chunk launch of 20480 chains x 26208 steps)",
+            "warp_inst_per_proposal": 14.9, "issue_active_pct": 67.7, "warps_active_per_scheduler": 7.0,
+            "registers_per_thread": 64, "smem_wavefronts_per_proposal": 3.1, "smem_wavefront_pct_of_peak": 53.3,
+            "dram_bytes_per_launch": 1.072e9, "algorithmic_bytes_per_launch": 1.073e9}
 
 
 class ClockSampler:
@@ -314,7 +316,7 @@ def main():
     hbm_peak = json.load(open(peaks_file))["hbm_gbs"] if os.path.isfile(peaks_file) else 6650.0
     roofline = {
         "bound": "issue", "achieved": achieved / 1e9, "peak": peak / 1e9, "unit": "Gwarp-inst/s",
-        "frac": achieved / peak, "traffic": None,
+        "frac": achieved / peak, "traffic": AS_BUILT["dram_bytes_per_launch"],
         "kernel": "spec_kernel<FULL=1,REPLAY=0,EARLY=0>", "i_alg_warp_inst_per_proposal": i_alg,
         "i_alg_formula": "(117 + 70*(1-(1-p)^32)) * p / (1-(1-p)^32), p = measured acceptance rate",
         "kernel_proposals_per_s": kernel_pps, "sm_clock_mhz_used": f_mhz, "sm_count": eng.sm_count,

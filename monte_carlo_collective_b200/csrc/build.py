@@ -13,7 +13,7 @@ HEADERS = ["anneal.cuh", "spec.cuh", "philox.cuh", os.path.join("..", "..", "inc
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-shared", "-Xcompiler", "-fPIC", "-diag-suppress", "550",
+    "-shared", "-Xcompiler", "-fPIC", "-diag-suppress", "550,177",
 ]
 
 

@@ -213,34 +213,56 @@ __global__ void __launch_bounds__(32) delta_kernel(const __grid_constant__ KArgs
 
 // Column sums of a [chain][step] history tile: per group, sum E and sum E^2 (experiments.py:593-595).
 // grid.x tiles the columns, grid.y slices the chains; partial sums go out with 64-bit atomics.
-template <typename T>
-__global__ void stats_kernel(const T *hist, long long pitch, int n_cols, long long h_origin, int n_chains,
-                             const int *group, const int *steps_done, unsigned long long *sum_e,
-                             unsigned long long *sum_e2, long long stat_pitch) {
-    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+// VEC consecutive columns per thread (16-byte loads when the tile is aligned), 4 chains in flight.
+template <typename T, int VEC>
+__global__ void __launch_bounds__(128) stats_kernel(const T *hist, long long pitch, int n_cols, long long h_origin, int n_chains,
+                                                    const int *group, const int *steps_done, unsigned long long *sum_e,
+                                                    unsigned long long *sum_e2, long long stat_pitch) {
+    const int col = (blockIdx.x * blockDim.x + threadIdx.x) * VEC;
     if (col >= n_cols) return;
+    const int nv = min(VEC, n_cols - col);      // valid columns of this thread (tail of the tile)
     const long long h = h_origin + col;
     const int per = (n_chains + gridDim.y - 1) / gridDim.y;
     const int c0 = blockIdx.y * per, c1 = min(n_chains, c0 + per);
-    unsigned long long s = 0, s2 = 0;
-    int cur = -1;
-    for (int c = c0; c < c1; ++c) {
-        const int gr = group ? group[c] : 0;
-        if (gr != cur) {
-            if (cur >= 0 && (s | s2)) {
-                atomicAdd(&sum_e[(size_t)cur * stat_pitch + h], s);
-                atomicAdd(&sum_e2[(size_t)cur * stat_pitch + h], s2);
+    unsigned long long s[VEC], s2[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) { s[v] = 0; s2[v] = 0; }
+    auto flush = [&](int g) {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v)
+            if (v < nv && (s[v] | s2[v])) {
+                atomicAdd(&sum_e[(size_t)g * stat_pitch + h + v], s[v]);
+                atomicAdd(&sum_e2[(size_t)g * stat_pitch + h + v], s2[v]);
+                s[v] = 0; s2[v] = 0;
             }
-            cur = gr; s = 0; s2 = 0;
+    };
+    struct alignas(sizeof(T) * VEC) Pack { T e[VEC]; };
+    int cur = c0 < c1 ? (group ? group[c0] : 0) : 0;
+    constexpr int U = 4;
+    for (int c = c0; c < c1; c += U) {
+        Pack p[U];
+        int gr[U], sd[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int cc = min(c + u, c1 - 1);
+            if (VEC > 1) p[u] = *reinterpret_cast<const Pack *>(hist + (size_t)cc * pitch + col);
+            else p[u].e[0] = hist[(size_t)cc * pitch + col];
+            gr[u] = group ? group[cc] : 0;
+            sd[u] = steps_done[cc];
         }
-        if (h > steps_done[c]) continue;  // early-stopped chain: no energy appended here
-        const unsigned long long v = (unsigned long long)hist[(size_t)c * pitch + col];
-        s += v; s2 += v * v;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (c + u >= c1) break;
+            if (gr[u] != cur) { flush(cur); cur = gr[u]; }
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+                // an early-stopped chain has no energy appended beyond its last step
+                const unsigned long long x = (h + v <= sd[u]) ? (unsigned long long)p[u].e[v] : 0ull;
+                s[v] += x; s2[v] += x * x;
+            }
+        }
     }
-    if (cur >= 0 && (s | s2)) {
-        atomicAdd(&sum_e[(size_t)cur * stat_pitch + h], s);
-        atomicAdd(&sum_e2[(size_t)cur * stat_pitch + h], s2);
-    }
+    flush(cur);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -778,7 +800,7 @@ int mcq_run(mcq_ctx *ctx, const mcq_run_params *p) {
         }
     } else if (p->chunk_steps > 0) chunk = p->chunk_steps;
     chunk = std::max(HBLK, chunk / HBLK * HBLK);
-    const long long chunk_pitch = (long long)chunk + 1;
+    const long long chunk_pitch = ((long long)chunk + 1 + 7) / 8 * 8;   // rows stay 16-byte aligned
     if (hkind != MCQ_HIST_NONE && !direct) {
         const size_t bytes = (size_t)nc * chunk_pitch * esz;
         if (ctx->buf[B_HIST0].ensure(bytes)) return fail(MCQ_ENOMEM, "device allocation failed (history chunk)");
@@ -838,11 +860,19 @@ int mcq_run(mcq_ctx *ctx, const mcq_run_params *p) {
                 hb += (size_t)lo * hp * esz;
                 const int n = hi - lo;
                 const int *grp = a.group ? a.group + lo : nullptr;
-                dim3 sg((n_cols + 127) / 128, std::max(1, std::min(64, n / 256)));
-                if (hkind == MCQ_HIST_U16)
-                    stats_kernel<uint16_t><<<sg, 128, 0, sb>>>(reinterpret_cast<const uint16_t *>(hb), hp, n_cols, h0, n, grp, a.steps_done + lo, d_sum_e, d_sum_e2, (long long)ns + 1);
-                else
-                    stats_kernel<int><<<sg, 128, 0, sb>>>(reinterpret_cast<const int *>(hb), hp, n_cols, h0, n, grp, a.steps_done + lo, d_sum_e, d_sum_e2, (long long)ns + 1);
+                // 16-byte column vectors when rows and the tile start are aligned (always true for the chunk buffer)
+                const bool vec_ok = (hp * esz) % 16 == 0 && (reinterpret_cast<uintptr_t>(hb) % 16) == 0;
+                const int vec = vec_ok ? (int)(16 / esz) : 1;
+                dim3 sg((n_cols + 128 * vec - 1) / (128 * vec), std::max(1, std::min(64, n / 64)));
+                if (hkind == MCQ_HIST_U16) {
+                    const uint16_t *h16 = reinterpret_cast<const uint16_t *>(hb);
+                    if (vec_ok) stats_kernel<uint16_t, 8><<<sg, 128, 0, sb>>>(h16, hp, n_cols, h0, n, grp, a.steps_done + lo, d_sum_e, d_sum_e2, (long long)ns + 1);
+                    else stats_kernel<uint16_t, 1><<<sg, 128, 0, sb>>>(h16, hp, n_cols, h0, n, grp, a.steps_done + lo, d_sum_e, d_sum_e2, (long long)ns + 1);
+                } else {
+                    const int *h32 = reinterpret_cast<const int *>(hb);
+                    if (vec_ok) stats_kernel<int, 4><<<sg, 128, 0, sb>>>(h32, hp, n_cols, h0, n, grp, a.steps_done + lo, d_sum_e, d_sum_e2, (long long)ns + 1);
+                    else stats_kernel<int, 1><<<sg, 128, 0, sb>>>(h32, hp, n_cols, h0, n, grp, a.steps_done + lo, d_sum_e, d_sum_e2, (long long)ns + 1);
+                }
                 CUDA_TRY(cudaGetLastError());
                 ++launches;
             }

@@ -41,7 +41,10 @@ def run(tag, mode, n, nc, ns, history="none", **kw):
 
 
 which = sys.argv[1] if len(sys.argv) > 1 else "base"
-if which == "base":
+if which == "quick32":
+    run("q", "full_3d", 12, 20480, 200000, algo="table")
+    run("q", "board", 12, 20480, 100000, algo="table")
+elif which == "base":
     for mode in ("full_3d", "board"):
         for G in (4, 8, 16, 32):
             run("G", mode, 12, 20480, 20000, lanes_per_chain=G)
