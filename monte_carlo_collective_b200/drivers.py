@@ -1,0 +1,147 @@
+"""The reference's experiment drivers, batched: one GPU launch per driver instead of one per call.
+
+`install()` (api.py) already lets the reference's own drivers run unchanged, but they call
+`run_experiment` once per beta pair / per N with n_runs = 5..20 chains, which leaves a B200 idle.
+The functions here keep the reference's names, argument meaning, seed conventions and result
+dictionaries (experiments.py:741-846, :943-1029, :1031-1201, competition.py:143-191) and fuse the
+outer loops into multi-group launches:
+
+* run_beta_start_end_pairs: every (beta_start, beta_end) pair is a schedule group of ONE launch;
+  chain r of pair idx keeps the seed base_seed + idx*1000 + r (experiments.py:791).
+* run_compare_beta_end: two such launches, the second with base_seed + 10000 (:1000).
+* measure_min_energy_vs_N: one launch per (init_mode, N), seeds base_seed + 10*idx +
+  sum(ord(c))%1000 + r (:1060-1067).
+* competition: best-of-R board search, best state written as `i,j,k` lines (competition.py:181-187).
+
+`plot=True` writes the CSV files the reference's plot functions write (reports.py); figures need
+matplotlib, which is outside the hot path.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import reports
+from . import schedules as _sched
+from .engine import BOARD, FULL, default_engine
+
+
+def _mode(mcmc_type):
+    return BOARD if mcmc_type == "board" else FULL
+
+
+def _patience(mode, early_stop_patience):
+    if mode != BOARD or early_stop_patience in (None, "None", "null"):
+        return None
+    return int(early_stop_patience)
+
+
+def run_beta_start_end_pairs(N, n_steps, beta_start_ends, annealing_type="linear_annealing", init_mode="random",
+                             n_runs=5, base_seed=0, verbose=True, plot=True, out_path=None, out_path_acceptance=None,
+                             mcmc_type="full_3d", early_stop_patience=100000, history="full", results_dir="results"):
+    """experiments.py:741-846.  history="full" returns per-chain histories like the reference;
+    history="stats" keeps only per-pair mean/std curves (what the plot consumes) for large n_runs."""
+    mode = _mode(mcmc_type)
+    pairs = [(float(a), float(b)) for a, b in beta_start_ends]
+    labels = [f"beta: {a}->{b}" for a, b in pairs]
+    tabs = np.stack([_sched.beta_table({"type": annealing_type, "beta_start": a, "beta_end": b}, n_steps) for a, b in pairs])
+    seeds = np.concatenate([base_seed + idx * 1000 + np.arange(n_runs) for idx in range(len(pairs))]).astype(np.uint64)
+    groups = np.repeat(np.arange(len(pairs), dtype=np.int32), n_runs)
+    res = default_engine().run(mode, N, n_steps, seeds, tabs, groups=groups, init_mode=init_mode, history=history,
+                               n_bins=100, early_stop_patience=_patience(mode, early_stop_patience), want_states=False)
+    out = {"all_histories": {}, "all_best_energies": {}, "mean_energy": {}, "std_energy": {}, "acceptance_rates": {}}
+    for idx, label in enumerate(labels):
+        sel = slice(idx * n_runs, (idx + 1) * n_runs)
+        best = [int(v) for v in res.best_energy[sel]]
+        out["all_best_energies"][label] = best
+        if history == "full":
+            rows = [res.energy_history[c, : int(res.steps_done[c]) + 1] for c in range(sel.start, sel.stop)]
+            out["all_histories"][label] = rows
+            if len({len(r) for r in rows}) == 1:
+                arr = np.array(rows, dtype=np.float64)
+                out["mean_energy"][label], out["std_energy"][label] = arr.mean(axis=0), arr.std(axis=0)
+        else:
+            out["mean_energy"][label], out["std_energy"][label] = reports.mean_std_from_sums(
+                res.stat_sum_e[idx], res.stat_sum_e2[idx], n_runs)
+        centers, rates = reports.acceptance_rates(res.accept_hist[sel].sum(axis=0), n_steps, n_runs)
+        out["acceptance_rates"][label] = (centers, rates)
+        if verbose:
+            for e in best:
+                print(e)
+            print(np.mean(best))
+        if plot and label in out["mean_energy"]:
+            reports.write_energy_csv(label, out["mean_energy"][label], out["std_energy"][label], results_dir)
+            if out_path_acceptance is not None:
+                reports.write_acceptance_csv(label, centers, rates, results_dir)
+    return out
+
+
+def run_compare_beta_end(Ns, n_steps, beta_start_ends, annealing_type="linear_annealing", init_mode="random", n_runs=5,
+                         base_seed=0, verbose=True, plot=True, out_path=None, mcmc_type="full_3d",
+                         early_stop_patience=100000, history="full", results_dir="results"):
+    """experiments.py:943-1029 (returns the two result dicts; the reference returns nothing and its plot call
+    raises a TypeError)."""
+    if len(Ns) != 2:
+        raise ValueError("Ns must contain exactly 2 values")
+    kw = dict(n_steps=n_steps, beta_start_ends=beta_start_ends, annealing_type=annealing_type, init_mode=init_mode,
+              n_runs=n_runs, verbose=verbose, plot=False, mcmc_type=mcmc_type, early_stop_patience=early_stop_patience,
+              history=history)
+    r1 = run_beta_start_end_pairs(N=Ns[0], base_seed=base_seed, **kw)
+    r2 = run_beta_start_end_pairs(N=Ns[1], base_seed=base_seed + 10000, **kw)
+    if plot:
+        for n, r in zip(Ns, (r1, r2)):
+            for label in r["mean_energy"]:
+                reports.write_energy_csv(f"N{n}_{label}", r["mean_energy"][label], r["std_energy"][label], results_dir)
+    return {Ns[0]: r1, Ns[1]: r2}
+
+
+def measure_min_energy_vs_N(Ns, n_steps, beta_schedule, schedule_params=None, init_modes=["random"], n_runs=5,
+                            base_seed=100, verbose=True, plot=True, out_path=None, mcmc_type="full_3d",
+                            early_stop_patience=100000, results_dir="results"):
+    """experiments.py:1031-1201: min energy and steps-to-best vs N for each initialisation."""
+    if isinstance(init_modes, str):
+        init_modes = [init_modes]
+    mode = _mode(mcmc_type)
+    betas = _sched.tabulate(beta_schedule, schedule_params, n_steps)
+    eng = default_engine()
+    results = {}
+    for init_mode in init_modes:
+        offset = sum(ord(c) for c in init_mode) % 1000
+        all_min, all_s2b = [], []
+        for idx, N in enumerate(Ns):
+            seeds = (base_seed + 10 * idx + offset + np.arange(n_runs)).astype(np.uint64)
+            r = eng.run(mode, N, n_steps, seeds, betas, init_mode=init_mode, history="none", want_states=False,
+                        early_stop_patience=_patience(mode, early_stop_patience))
+            all_min.append(np.array(r.best_energy, dtype=np.int64))
+            all_s2b.append(np.array(r.steps_to_best, dtype=np.int64))
+            if verbose:
+                print(all_min[-1].mean())
+        results[init_mode] = {
+            "mean_min_energies": np.array([a.mean() for a in all_min]), "std_min_energies": np.array([a.std() for a in all_min]),
+            "all_min_energies": all_min,
+            "mean_steps_to_best": np.array([a.mean() for a in all_s2b]), "std_steps_to_best": np.array([a.std() for a in all_s2b]),
+            "all_steps_to_best": all_s2b,
+        }
+        if plot:
+            reports.write_vs_n_csv("min_energy", init_mode, Ns, results[init_mode]["mean_min_energies"],
+                                   results[init_mode]["std_min_energies"], results_dir)
+            reports.write_vs_n_csv("steps_to_best", init_mode, Ns, results[init_mode]["mean_steps_to_best"],
+                                   results[init_mode]["std_steps_to_best"], results_dir)
+    return {"Ns": Ns, "results": results}   # experiments.py:1198-1201
+
+
+def competition(N=15, n_runs=10, n_steps=100000, beta_start=1.0, beta_end=3.0, base_seed=42, init_mode="random",
+                early_stop_patience=None, out_dir="competition_results", verbose=True, stamp=None):
+    """competition.py:143-191: best-of-R board chains, best heights written as `i,j,k` lines.
+    n_runs can be thousands here; the file format and the seed rule (base_seed + r) are the reference's."""
+    betas = _sched.beta_table({"type": "linear_annealing", "beta_start": beta_start, "beta_end": beta_end}, n_steps)
+    seeds = (base_seed + np.arange(n_runs)).astype(np.uint64)
+    r = default_engine().run(BOARD, N, n_steps, seeds, betas, init_mode=init_mode, history="none",
+                             early_stop_patience=early_stop_patience)
+    order = np.argsort(r.best_energy, kind="stable")
+    results = [{"run_idx": int(c), "best_energy": int(r.best_energy[c]), "best_state": r.best_state[c].astype(np.int64),
+                "steps_to_best": int(r.steps_to_best[c])} for c in order]
+    if verbose:
+        print("Best energies: ", [x["best_energy"] for x in results[:20]])
+        print(results[0]["best_state"])
+    path = reports.write_best_heights(results[0]["best_state"], out_dir, stamp)
+    return results, path

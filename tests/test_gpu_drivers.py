@@ -1,0 +1,106 @@
+"""GPU: batched experiment drivers: seed conventions, result shapes, CSV schemas."""
+import os
+
+import numpy as np
+import pandas as pd
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def mcq(engine):
+    import monte_carlo_collective_b200 as m
+    from monte_carlo_collective_b200 import engine as eng_mod
+    eng_mod._default = engine
+    return m
+
+
+def test_beta_pairs_equal_per_pair_run_experiment(mcq, tmp_path):
+    from monte_carlo_collective_b200 import drivers
+    pairs = [[0.5, 3.0], [0.1, 5.0], [1.0, 5.0]]            # config.yaml:28
+    out = drivers.run_beta_start_end_pairs(N=8, n_steps=4000, beta_start_ends=pairs, annealing_type="linear_annealing",
+                                           init_mode="random", n_runs=6, base_seed=42, verbose=False, plot=True,
+                                           out_path="x.png", out_path_acceptance="y.png", mcmc_type="board",
+                                           early_stop_patience=None, results_dir=str(tmp_path))
+    assert list(out["all_histories"]) == ["beta: 0.5->3.0", "beta: 0.1->5.0", "beta: 1.0->5.0"]
+    for idx, (b0, b1) in enumerate(pairs):
+        label = f"beta: {b0}->{b1}"
+        sp = {"type": "linear_annealing", "beta_start": b0, "beta_end": b1}
+        hist, best, _t, acc, _rej, _s = mcq.run_experiment(8, 4000, "random", None, 6, base_seed=42 + idx * 1000,
+                                                           schedule_params=sp, mcmc_type="board", early_stop_patience=None)
+        assert (np.array(out["all_histories"][label]) == np.array(hist)).all()       # the fused launch is the same chains
+        assert out["all_best_energies"][label] == best
+        df = pd.read_csv(tmp_path / f"{label}.csv")
+        assert list(df.columns) == ["step", "mean_energy", "std_energy"] and len(df) == 4001
+        assert np.allclose(df["mean_energy"], np.array(hist, dtype=float).mean(axis=0))
+        assert np.allclose(df["std_energy"], np.array(hist, dtype=float).std(axis=0))
+        da = pd.read_csv(tmp_path / f"acceptance_rates_{label}.csv")
+        assert list(da.columns) == ["bin_center", "acceptance_rate"] and len(da) == 100
+        # the reference's binning of accepted / rejected step lists (experiments.py:669-700)
+        edges = np.linspace(0, 4000, 101)
+        a = np.concatenate(acc)
+        want = [np.sum((a >= edges[b]) & (a < edges[b + 1])) / (6 * 40) for b in range(100)]
+        assert np.allclose(da["acceptance_rate"], want)
+    # hotter start accepts more at the beginning (0.82 vs 0.45 in the first bin at N=12)
+    first_bin = {k: v[1][0] for k, v in out["acceptance_rates"].items()}
+    assert first_bin["beta: 0.1->5.0"] > first_bin["beta: 0.5->3.0"] > first_bin["beta: 1.0->5.0"]
+
+
+def test_beta_pairs_stats_mode_matches_full(mcq):
+    from monte_carlo_collective_b200 import drivers
+    kw = dict(N=6, n_steps=1500, beta_start_ends=[[1.0, 3.0], [1.0, 5.0]], annealing_type="exponential_annealing",
+              n_runs=40, base_seed=7, verbose=False, plot=False, mcmc_type="full_3d")
+    full = drivers.run_beta_start_end_pairs(history="full", **kw)
+    st = drivers.run_beta_start_end_pairs(history="stats", **kw)
+    for label in full["mean_energy"]:
+        assert np.allclose(full["mean_energy"][label], st["mean_energy"][label])
+        assert np.allclose(full["std_energy"][label], st["std_energy"][label], atol=1e-9)
+        assert full["all_best_energies"][label] == st["all_best_energies"][label]
+
+
+def test_compare_beta_end_and_min_energy_vs_n(mcq, tmp_path):
+    from monte_carlo_collective_b200 import drivers
+    with pytest.raises(ValueError):
+        drivers.run_compare_beta_end([12], 10, [[1.0, 3.0]])
+    out = drivers.run_compare_beta_end([5, 7], 800, [[1.0, 3.0], [1.0, 5.0]], annealing_type="exponential_annealing",
+                                       n_runs=4, base_seed=42, verbose=False, plot=True, mcmc_type="board",
+                                       early_stop_patience="None", results_dir=str(tmp_path))
+    sp = {"type": "exponential_annealing", "beta_start": 1.0, "beta_end": 5.0}
+    _h, best, *_ = mcq.run_experiment(7, 800, "random", None, 4, base_seed=42 + 10000 + 1000, schedule_params=sp,
+                                      mcmc_type="board", early_stop_patience=None)
+    assert out[7]["all_best_energies"]["beta: 1.0->5.0"] == best                 # experiments.py:1000 and :791
+    assert os.path.isfile(tmp_path / "N5_beta: 1.0->3.0.csv")
+
+    Ns = [3, 4, 5, 11]
+    sp = {"type": "linear_annealing", "beta_start": 1.0, "beta_end": 3.0}
+    res = drivers.measure_min_energy_vs_N(Ns, 3000, None, schedule_params=sp, init_modes=["random", "klarner", "latin"],
+                                          n_runs=8, base_seed=100, verbose=False, plot=True, mcmc_type="board",
+                                          early_stop_patience=None, results_dir=str(tmp_path))
+    assert res["Ns"] == Ns
+    res = res["results"]
+    assert list(res) == ["random", "klarner", "latin"]
+    for init in res:
+        off = sum(ord(c) for c in init) % 1000
+        for idx, n in enumerate(Ns):
+            _h, best, _t, _a, _r, s2b = mcq.run_experiment(n, 3000, init, None, 8, base_seed=100 + 10 * idx + off,
+                                                          schedule_params=sp, mcmc_type="board", early_stop_patience=None)
+            assert res[init]["all_min_energies"][idx].tolist() == best           # experiments.py:1060-1067
+            assert res[init]["all_steps_to_best"][idx].tolist() == s2b
+        df = pd.read_csv(tmp_path / f"min_energy_vs_N_{init}.csv")
+        assert list(df.columns) == ["N", f"{init}_mean_min_energy", f"{init}_std_min_energy"]
+        ds = pd.read_csv(tmp_path / f"steps_to_best_vs_N_{init}.csv")
+        assert list(ds.columns) == ["N", f"{init}_mean_steps_to_best", f"{init}_std_steps_to_best"]
+    # Klarner's construction is a solution when gcd(N,210) == 1: energy 0 from step 0 (report section IV-C)
+    assert res["klarner"]["mean_min_energies"][3] == 0 and res["klarner"]["mean_steps_to_best"][3] == 0
+
+
+def test_competition_flow(mcq, engine, tmp_path):
+    from monte_carlo_collective_b200 import drivers
+    results, path = drivers.competition(N=9, n_runs=64, n_steps=20000, out_dir=str(tmp_path), verbose=False, stamp="t")
+    assert os.path.basename(path) == "best_heights_9_t.txt"
+    lines = open(path).read().split()
+    assert len(lines) == 81 and lines[0].startswith("0,0,") and lines[-1].startswith("8,8,")
+    h = np.array([int(x.split(",")[2]) for x in lines]).reshape(9, 9)
+    assert [r["best_energy"] for r in results] == sorted(r["best_energy"] for r in results)
+    assert int(engine.energy("board", 9, h[None].astype(np.uint8))[0]) == results[0]["best_energy"]
