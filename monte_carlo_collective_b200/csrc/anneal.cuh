@@ -50,7 +50,8 @@ struct SLayout {
     int tbl;        // table bytes (N^3 + 1 scratch byte, rounded up to 4)
     int off_state;  // board: heights; full_3d: uint32 per queen = cell id | wide id << 16
     int off_occ;    // full_3d: occupancy bitset
-    int off_rec;    // lane-0 scalars (RecSlot)
+    int off_rec;    // spare words
+    int off_ring;   // ring of Philox words: 64 steps x 16 B
     int stride;     // slab size, multiple of 16
     int nbr_len;    // neighbour-row length: families*(N-1) rounded up to 32
     int rounds;     // nbr_len / 32

@@ -95,7 +95,8 @@ static SLayout make_spec_layout(int full, int N, int Q) {
     L.off_occ = round_up(L.off_state + state_b, 4);
     const int occ_b = full ? (N * N * N + 31) / 32 * 4 : 0;
     L.off_rec = L.off_occ + occ_b;
-    L.stride = round_up(L.off_rec + 8 * 4, 16);
+    L.off_ring = round_up(L.off_rec + 8 * 4, 16);
+    L.stride = L.off_ring + 64 * 16;
     L.nbr_len = round_up((full ? NFAM : NFAM - 1) * (N - 1), 32);
     L.rounds = L.nbr_len / 32;
     const int W = 2 * N - 1;

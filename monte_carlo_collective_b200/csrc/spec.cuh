@@ -270,6 +270,8 @@ __global__ void __launch_bounds__(128, MCQ_SPEC_MINB) spec_kernel(const __grid_c
     const double *un_row = REPLAY ? a.runif + (size_t)chain_c * a.n_steps : nullptr;
     int bin = a.bin_at_begin;
     int next_edge = a.n_bins > 0 ? a.bin_starts[bin + 1] : 0x7fffffff;
+    const int sG = sT + a.sl.off_ring;   // ring of random words: 64 steps x 16 B
+    [[maybe_unused]] int tfill = t;       // steps < tfill of this chain have their words in the ring
     [[maybe_unused]] uint32_t near = 0u;
     // history row, addressed by history index h = step + 1 (h_origin = index held by column 0)
     unsigned char *hrow = static_cast<unsigned char *>(a.hist) +
@@ -317,7 +319,19 @@ __global__ void __launch_bounds__(128, MCQ_SPEC_MINB) spec_kernel(const __grid_c
             near_flag = !bad && fabs(u64 - p) < 1e-6;
         } else {
             const float cb = __ldg(beta_row + s);
-            const Philox4 r = philox4x32_10((uint32_t)s, 0u, 0u, PHILOX_DOMAIN_STEP, key0, key1);
+            // Random words of step s come from a 64-step ring in the slab: a round consumes only the
+            // steps it commits, so one Philox4x32-10 call per lane refills LPC steps that are all used,
+            // instead of recomputing the discarded lanes' words every round.
+            if (active && tfill < t + LPC) {
+                const Philox4 w = philox4x32_10((uint32_t)(tfill + sub), 0u, 0u, PHILOX_DOMAIN_STEP, key0, key1);
+                asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(sbase + (uint32_t)(sG + 16 * ((tfill + sub) & 63))),
+                             "r"(w.x), "r"(w.y), "r"(w.z), "r"(w.w) : "memory");
+                tfill += LPC;
+            }
+            __syncwarp();
+            Philox4 r;
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                         : "r"(sbase + (uint32_t)(sG + 16 * (s & 63))));
             if (FULL) {
                 const uint32_t N3 = (uint32_t)(N * N * N);
                 const uint32_t q = __umulhi(r.x, (uint32_t)a.Q);
