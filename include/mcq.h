@@ -157,7 +157,10 @@ int mcq_energy(mcq_ctx *ctx, int mode, int n, int q, int n_states, const uint8_t
 /*
  * Delta energies of candidate moves evaluated with the kernel's line-occupancy counters,
  * without applying them.  moves use the replay packing; out_delta[b][m] = conflicts(new) -
- * conflicts(old) exactly as experiments.py:235 / :323 compute it.
+ * conflicts(old) exactly as experiments.py:235 / :323 compute it.  A move whose queen index or
+ * coordinates are out of range yields INT32_MIN.  Malformed states (height or coordinate out of
+ * range, two queens on one cell) make mcq_energy / mcq_delta_energy / mcq_run return MCQ_EINVAL,
+ * as the reference's state constructors raise ValueError (mcmc.py:113-118, mcmc_board.py:62-65).
  */
 int mcq_delta_energy(mcq_ctx *ctx, int mode, int n, int q, int n_states, const uint8_t *states,
                      int n_moves, const uint32_t *moves, int32_t *out_delta, int mem, void *stream);

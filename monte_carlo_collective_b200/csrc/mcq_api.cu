@@ -4,6 +4,7 @@
 // pool -- start n_runs chains, collect histories / best energies / accept lists -- is done here
 // as a handful of kernel launches over a batch of chains resident in shared memory.
 #include <cuda_runtime.h>
+#include <limits.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -178,6 +179,33 @@ __global__ void init_states_kernel(int full, int N, int Q, int init_mode, int n_
     }
 }
 
+// Explicit states are validated like the reference's constructors do (heights in range,
+// mcmc_board.py:64-65; cells in range and pairwise distinct, mcmc.py:113-118): one thread per state,
+// duplicates found with a scratch occupancy bitset.  *bad counts the offending states.
+__global__ void validate_states_kernel(int full, int N, int Q, int n_states, const uint8_t *state, int state_bytes,
+                                       uint32_t *occ_scratch, int occ_words, unsigned *bad) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_states) return;
+    const uint8_t *st = state + (size_t)b * state_bytes;
+    bool ok = true;
+    if (!full) {
+        for (int c = 0; c < N * N; ++c) ok = ok && st[c] < N;
+    } else {
+        uint32_t *occ = occ_scratch + (size_t)b * occ_words;
+        for (int w = 0; w < occ_words; ++w) occ[w] = 0u;
+        for (int q = 0; q < Q && ok; ++q) {
+            const int i = st[3 * q], j = st[3 * q + 1], k = st[3 * q + 2];
+            ok = i < N && j < N && k < N;
+            if (ok) {
+                const int cid = (i * N + j) * N + k;
+                ok = !((occ[cid >> 5] >> (cid & 31)) & 1u);
+                occ[cid >> 5] |= 1u << (cid & 31);
+            }
+        }
+    }
+    if (!ok) atomicAdd(bad, 1u);
+}
+
 // one warp per state: E = sum over attack lines of C(count,2)
 __global__ void __launch_bounds__(32) energy_kernel(const __grid_constant__ KArgs a, int *out) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -198,13 +226,20 @@ __global__ void __launch_bounds__(32) delta_kernel(const __grid_constant__ KArgs
     for (int m = 0; m < n_moves; ++m) {
         const uint32_t w = moves[(size_t)b * n_moves + m];
         int i0, j0, k0, i1, j1, k1;
+        bool bad;
         if (a.full) {
             const int q = w & 0xfff;
             i1 = (w >> 12) & 63; j1 = (w >> 18) & 63; k1 = (w >> 24) & 63;
-            unpack_pos(a.lay.pos32, load_pos(st, a.lay.pos32, q), i0, j0, k0);
+            bad = q >= a.Q || i1 >= a.N || j1 >= a.N || k1 >= a.N;
+            unpack_pos(a.lay.pos32, load_pos(st, a.lay.pos32, bad ? 0 : q), i0, j0, k0);
         } else {
             i0 = i1 = w & 255; j0 = j1 = (w >> 8) & 255; k1 = (w >> 16) & 255;
-            k0 = st[i0 * a.N + j0];
+            bad = i0 >= a.N || j0 >= a.N || k1 >= a.N;
+            k0 = st[bad ? 0 : i0 * a.N + j0];
+        }
+        if (bad) {   // out-of-range move: flagged, never evaluated
+            if (g == 0) out[(size_t)b * n_moves + m] = INT_MIN;
+            continue;
         }
         LineEval<32> ev;
         const int d = group_sum<32>(ev.eval(L, smem, i0, j0, k0, i1, j1, k1));
@@ -387,6 +422,24 @@ static int copy_out(void *dst, const void *src_dev, size_t bytes, int mem, cudaS
     return 0;
 }
 
+// returns MCQ_EINVAL when a state is malformed (the reference raises ValueError in its constructors)
+static int validate_states(mcq_ctx *ctx, int full, int n, int q, int n_states, const uint8_t *d_states, int sbytes,
+                           uint32_t *d_counter, cudaStream_t s) {
+    const int occ_words = full ? (n * n * n + 31) / 32 : 0;
+    if (full && ctx->buf[B_OCC].ensure((size_t)n_states * occ_words * 4)) return fail(MCQ_ENOMEM, "device allocation failed");
+    CUDA_TRY(cudaMemsetAsync(d_counter, 0, 4, s));
+    validate_states_kernel<<<(n_states + 127) / 128, 128, 0, s>>>(full, n, q, n_states, d_states, sbytes,
+                                                                  static_cast<uint32_t *>(ctx->buf[B_OCC].p), occ_words, d_counter);
+    CUDA_TRY(cudaGetLastError());
+    unsigned bad = 0;
+    CUDA_TRY(cudaMemcpyAsync(&bad, d_counter, 4, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    CUDA_TRY(cudaMemsetAsync(d_counter, 0, 4, s));
+    if (bad) return fail(MCQ_EINVAL, full ? "initial state: a cell is out of range or two queens occupy the same (i,j,k) cell"
+                                          : "initial state: all heights must be in [0, N-1]");
+    return 0;
+}
+
 }  // namespace mcq
 
 using namespace mcq;
@@ -495,6 +548,10 @@ static int probe_common(mcq_ctx *ctx, int mode, int n, int q, int n_states, cons
     void *d = nullptr;
     if (int rc = stage_in(ctx, B_STATE_IN, states, (size_t)n_states * a.state_bytes, mem, s, &d)) return rc;
     a.state = static_cast<uint8_t *>(d);
+    if (n_states > 0) {
+        if (ctx->buf[B_REC].ensure(64)) return fail(MCQ_ENOMEM, "device allocation failed");
+        if (int rc = validate_states(ctx, a.full, n, q, n_states, a.state, a.state_bytes, static_cast<uint32_t *>(ctx->buf[B_REC].p), s)) return rc;
+    }
     return 0;
 }
 
@@ -730,6 +787,8 @@ int mcq_run(mcq_ctx *ctx, const mcq_run_params *p) {
     if (p->init_mode == MCQ_INIT_EXPLICIT) {
         CUDA_TRY(cudaMemcpyAsync(a.state, p->init_states, (size_t)nc * sbytes,
                                  mem == MCQ_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
+        if (int rc = validate_states(ctx, full, p->n, p->q, nc, a.state, sbytes, a.replay_err, s)) return rc;
+        ++launches;
     } else {
         const int occ_words = full ? (p->n * p->n * p->n + 31) / 32 : 0;
         if (full && ctx->buf[B_OCC].ensure((size_t)nc * occ_words * 4)) return fail(MCQ_ENOMEM, "device allocation failed");

@@ -101,3 +101,26 @@ def test_delta_energy_equals_energy_difference(engine):
         e0 = int(engine.energy("full_3d", n, c[None])[0])
         e1 = engine.energy("full_3d", n, np.array(after))
         assert (e1 - e0).tolist() == d.tolist()
+
+
+def test_malformed_states_and_moves_are_rejected(engine):
+    """The reference's constructors raise ValueError (mcmc.py:113-118, mcmc_board.py:62-65); so does the ABI."""
+    n = 5
+    good_h = np.zeros((n, n), dtype=np.uint8)
+    bad_h = good_h.copy(); bad_h[2, 3] = n
+    with pytest.raises(ValueError, match="heights"):
+        engine.energy("board", n, np.stack([good_h, bad_h]))
+    cells = np.array([[i, j, (i + j) % n] for i in range(n) for j in range(n)], dtype=np.uint8)
+    dup = cells.copy(); dup[7] = dup[3]
+    oob = cells.copy(); oob[0, 2] = n
+    for bad in (dup, oob):
+        with pytest.raises(ValueError, match="cell"):
+            engine.energy("full_3d", n, np.stack([cells, bad]))
+        with pytest.raises(ValueError):
+            engine.run("full_3d", n, 10, np.arange(2, dtype=np.uint64), np.ones((1, 10)), init_states=np.stack([cells, bad]))
+    with pytest.raises(ValueError):
+        engine.run("board", n, 10, np.arange(1, dtype=np.uint64), np.ones((1, 10)), init_states=bad_h[None])
+    d = engine.delta_energy("board", n, good_h[None], np.array([[[0, 0, 1], [0, n, 1], [0, 0, n]]]))
+    assert d[0, 1] == np.iinfo(np.int32).min and d[0, 2] == np.iinfo(np.int32).min
+    d = engine.delta_energy("full_3d", n, cells[None], np.array([[[0, 1, 1, 1], [n * n, 0, 0, 0], [0, n, 0, 0]]]))
+    assert d[0, 1] == np.iinfo(np.int32).min and d[0, 2] == np.iinfo(np.int32).min and d[0, 0] != np.iinfo(np.int32).min
