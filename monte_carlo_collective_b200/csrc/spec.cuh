@@ -435,10 +435,31 @@ __global__ void __launch_bounds__(128, MCQ_SPEC_MINB) spec_kernel(const __grid_c
                 bc0 = __shfl_sync(FULLMASK, wc0, hl); bc1 = __shfl_sync(FULLMASK, wc1, hl); baux = __shfl_sync(FULLMASK, waux, hl);
                 bT = a.sl.cta_bytes + (slab0 + hl / LPC) * a.sl.stride;
             }
-            table_lines_add<NR>(sbase + (uint32_t)bT, a.nbr, bc0 * (uint32_t)L + (uint32_t)lane, rounds, -1);
-            if (lane == 0) SM8(bT + bc0) = (unsigned char)(SM8(bT + bc0) - NF);
-            __syncwarp();
-            table_lines_add<NR>(sbase + (uint32_t)bT, a.nbr, bc1 * (uint32_t)L + (uint32_t)lane, rounds, +1);
+            if constexpr (NR > 0) {
+                // both neighbour rows are fetched before the first phase so that only one L2 round trip is exposed
+                uint32_t ra[NR], rb[NR];
+#pragma unroll
+                for (int r = 0; r < NR; ++r) ra[r] = __ldg(a.nbr + bc0 * (uint32_t)L + (uint32_t)lane + r * 32);
+#pragma unroll
+                for (int r = 0; r < NR; ++r) rb[r] = __ldg(a.nbr + bc1 * (uint32_t)L + (uint32_t)lane + r * 32);
+#pragma unroll
+                for (int r = 0; r < NR; ++r) {
+                    const SmRef<unsigned char> cell{sbase + (uint32_t)bT + ra[r]};
+                    cell = (unsigned char)((unsigned char)cell - 1);
+                }
+                if (lane == 0) SM8(bT + bc0) = (unsigned char)(SM8(bT + bc0) - NF);
+                __syncwarp();
+#pragma unroll
+                for (int r = 0; r < NR; ++r) {
+                    const SmRef<unsigned char> cell{sbase + (uint32_t)bT + rb[r]};
+                    cell = (unsigned char)((unsigned char)cell + 1);
+                }
+            } else {
+                table_lines_add<NR>(sbase + (uint32_t)bT, a.nbr, bc0 * (uint32_t)L + (uint32_t)lane, rounds, -1);
+                if (lane == 0) SM8(bT + bc0) = (unsigned char)(SM8(bT + bc0) - NF);
+                __syncwarp();
+                table_lines_add<NR>(sbase + (uint32_t)bT, a.nbr, bc1 * (uint32_t)L + (uint32_t)lane, rounds, +1);
+            }
             if (lane == 0) {
                 SM8(bT + bc1) = (unsigned char)(SM8(bT + bc1) + NF);
                 const int bP = bT + a.sl.off_state;
