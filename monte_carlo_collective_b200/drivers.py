@@ -94,25 +94,50 @@ def run_compare_beta_end(Ns, n_steps, beta_start_ends, annealing_type="linear_an
     return {Ns[0]: r1, Ns[1]: r2}
 
 
+_POOL = {}
+
+
+def _pool_engine():
+    """One engine (context + stream) per worker thread, so independent problems overlap on the GPU."""
+    import threading
+    from .engine import Engine
+    tid = threading.get_ident()
+    if tid not in _POOL:
+        _POOL[tid] = Engine(default_engine().device)
+    return _POOL[tid]
+
+
 def measure_min_energy_vs_N(Ns, n_steps, beta_schedule, schedule_params=None, init_modes=["random"], n_runs=5,
                             base_seed=100, verbose=True, plot=True, out_path=None, mcmc_type="full_3d",
-                            early_stop_patience=100000, results_dir="results"):
-    """experiments.py:1031-1201: min energy and steps-to-best vs N for each initialisation."""
+                            early_stop_patience=100000, results_dir="results", workers=8):
+    """experiments.py:1031-1201: min energy and steps-to-best vs N for each initialisation.
+
+    Every (init_mode, N) point is its own batch of n_runs chains; the points are independent, so they are
+    issued from `workers` host threads (one engine / CUDA stream each) and run concurrently on the GPU."""
+    from concurrent.futures import ThreadPoolExecutor
     if isinstance(init_modes, str):
         init_modes = [init_modes]
     mode = _mode(mcmc_type)
     betas = _sched.tabulate(beta_schedule, schedule_params, n_steps)
-    eng = default_engine()
+
+    def point(job):
+        init_mode, idx, N = job
+        offset = sum(ord(c) for c in init_mode) % 1000
+        seeds = (base_seed + 10 * idx + offset + np.arange(n_runs)).astype(np.uint64)
+        r = _pool_engine().run(mode, N, n_steps, seeds, betas, init_mode=init_mode, history="none", want_states=False,
+                               early_stop_patience=_patience(mode, early_stop_patience))
+        return np.array(r.best_energy, dtype=np.int64), np.array(r.steps_to_best, dtype=np.int64)
+
+    jobs = [(init_mode, idx, N) for init_mode in init_modes for idx, N in enumerate(Ns)]
+    with ThreadPoolExecutor(max_workers=max(1, workers)) as ex:
+        done = dict(zip(jobs, ex.map(point, jobs)))
     results = {}
     for init_mode in init_modes:
-        offset = sum(ord(c) for c in init_mode) % 1000
         all_min, all_s2b = [], []
         for idx, N in enumerate(Ns):
-            seeds = (base_seed + 10 * idx + offset + np.arange(n_runs)).astype(np.uint64)
-            r = eng.run(mode, N, n_steps, seeds, betas, init_mode=init_mode, history="none", want_states=False,
-                        early_stop_patience=_patience(mode, early_stop_patience))
-            all_min.append(np.array(r.best_energy, dtype=np.int64))
-            all_s2b.append(np.array(r.steps_to_best, dtype=np.int64))
+            mins, s2b = done[(init_mode, idx, N)]
+            all_min.append(mins)
+            all_s2b.append(s2b)
             if verbose:
                 print(all_min[-1].mean())
         results[init_mode] = {
