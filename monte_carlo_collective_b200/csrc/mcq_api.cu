@@ -735,8 +735,10 @@ int mcq_run(mcq_ctx *ctx, const mcq_run_params *p) {
         DevBuf &nb = ctx->nbr[full * 256 + p->n];
         if (!nb.p) {
             const int cells = p->n * p->n * p->n;
-            if (nb.ensure((size_t)cells * sl.nbr_len * 2)) return fail(MCQ_ENOMEM, "device allocation failed (neighbour lists)");
-            build_neighbours_kernel<<<(cells + 127) / 128, 128, 0, s>>>(full, p->n, sl.nbr_len, static_cast<uint16_t *>(nb.p));
+            if (nb.ensure((size_t)cells * sl.nbr_len * 2) || ctx->buf[B_MOVES].ensure((size_t)cells * sl.nbr_len * 2))
+                return fail(MCQ_ENOMEM, "device allocation failed (neighbour lists)");
+            build_neighbours_kernel<<<(cells + 127) / 128, 128, 0, s>>>(full, p->n, sl.nbr_len, static_cast<uint16_t *>(nb.p),
+                                                                       static_cast<uint16_t *>(ctx->buf[B_MOVES].p));
             CUDA_TRY(cudaGetLastError());
             ++launches;
         }

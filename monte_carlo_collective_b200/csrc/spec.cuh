@@ -57,11 +57,12 @@ __host__ __device__ inline void family_dir(int f, int &dx, int &dy, int &dz) {
 // ---- geometry tables, built once per (mode, N) and shared by every chain ----------------------
 // nbr[cell][L]: ids of all cells on the attack lines through `cell` (itself excluded), padded to a
 // multiple of 32 with the id N^3, a scratch byte at the end of every T, so updates need no predicate.
-__global__ void build_neighbours_kernel(int full, int N, int L, uint16_t *nbr) {
+__global__ void build_neighbours_kernel(int full, int N, int L, uint16_t *nbr, uint16_t *tmp) {
     const int cell = blockIdx.x * blockDim.x + threadIdx.x;
     if (cell >= N * N * N) return;
     const int x = cell / (N * N), y = (cell / N) % N, z = cell % N;
     uint16_t *row = nbr + (size_t)cell * L;
+    uint16_t *list = tmp + (size_t)cell * L;   // unordered neighbours
     int n = 0;
     for (int f = full ? 0 : 1; f < NFAM; ++f) {
         int dx, dy, dz;
@@ -70,10 +71,39 @@ __global__ void build_neighbours_kernel(int full, int N, int L, uint16_t *nbr) {
             if (tau == 0) continue;
             const int u = x + tau * dx, v = y + tau * dy, w = z + tau * dz;
             if ((unsigned)u < (unsigned)N && (unsigned)v < (unsigned)N && (unsigned)w < (unsigned)N)
-                row[n++] = (uint16_t)((u * N + v) * N + w);
+                list[n++] = (uint16_t)((u * N + v) * N + w);
         }
     }
-    for (; n < L; ++n) row[n] = (uint16_t)(N * N * N);
+    // Order the row so that the 32 entries one warp instruction touches fall into distinct shared-memory
+    // banks where possible (byte table: bank = (id / 4) % 32; ids in the same 4-byte word do not conflict).
+    // Greedy: each group of 32 takes at most one word per bank; leftovers fill the remaining slots.
+    const uint16_t PAD = (uint16_t)(N * N * N), TAKEN = 0xffffu;
+    int placed = 0;
+    for (int g = 0; g < L / 32; ++g) {
+        unsigned banks = 0u;
+        int word_of_bank[32];
+        int k = 0;
+        for (int e = 0; e < n && k < 32; ++e) {
+            if (list[e] == TAKEN) continue;
+            const int word = list[e] >> 2, bank = word & 31;
+            if ((banks >> bank) & 1u) { if (word_of_bank[bank] != word) continue; }
+            else { banks |= 1u << bank; word_of_bank[bank] = word; }
+            row[g * 32 + k++] = list[e];
+            list[e] = TAKEN;
+            ++placed;
+        }
+        // not enough conflict-free entries for this group: top up with whatever is left only in the last
+        // groups (keeps early groups conflict-free); here simply leave the rest of the group as padding
+        for (; k < 32; ++k) row[g * 32 + k] = PAD;
+    }
+    // anything still unplaced (more than L/32 entries in one bank): overwrite padding slots from the end
+    for (int e = 0, slot = L - 1; e < n && placed < n; ++e) {
+        if (list[e] == TAKEN) continue;
+        while (slot >= 0 && row[slot] != PAD) --slot;
+        row[slot] = list[e];
+        list[e] = TAKEN;
+        ++placed;
+    }
 }
 
 // wide[c] = i*W^2 + j*W + k (W = 2N-1): the difference of two wide ids identifies (di,dj,dk);
