@@ -90,11 +90,11 @@ static Layout make_layout(int full, int N, int Q, int G) {
 
 static SLayout make_spec_layout(int full, int N, int Q) {
     SLayout L;
-    L.tbl = round_up(N * N * N + 1, 4);
+    L.tbl = round_up((N * N * N + 1) * (full ? 2 : 1), 4);   // full_3d: uint16 entries (count | occupied << 15)
     L.off_state = L.tbl;
     const int state_b = full ? Q * 4 : N * N;
     L.off_occ = round_up(L.off_state + state_b, 4);
-    const int occ_b = full ? (N * N * N + 31) / 32 * 4 : 0;
+    const int occ_b = 0;   // the occupancy flag lives in the table entries
     L.off_rec = L.off_occ + occ_b;
     L.off_ring = round_up(L.off_rec + 8 * 4, 16);
     L.stride = L.off_ring + 64 * 16;
@@ -107,8 +107,9 @@ static SLayout make_spec_layout(int full, int N, int Q) {
     return L;
 }
 
-// uint8 table entries hold at most 13*N (full_3d) / 12*N (board)
-static inline bool spec_eligible(int full, int N) { return (full ? 13 : 12) * N <= 255; }
+// board: uint8 entries hold at most 12*N; full_3d: uint16 entries, bounded by the neighbour-row length
+// the kernels are compiled for (13*(N-1) <= 256) and the 16-bit cell / wide ids
+static inline bool spec_eligible(int full, int N) { return full ? 13 * (N - 1) <= 256 : 12 * N <= 255; }
 
 static inline int state_bytes_of(int mode, int n, int q) { return mode == MCQ_MODE_FULL3D ? 3 * q : n * n; }
 
@@ -637,7 +638,7 @@ int mcq_run(mcq_ctx *ctx, const mcq_run_params *p) {
     int G = p->lanes_per_chain;
     if (G != 0 && G != 4 && G != 8 && G != 16 && G != 32) return fail(MCQ_EINVAL, "lanes_per_chain must be 0, 4, 8, 16 or 32");
     if (p->algo < MCQ_ALGO_AUTO || p->algo > MCQ_ALGO_TABLE) return fail(MCQ_EINVAL, "unknown algo");
-    if (p->algo == MCQ_ALGO_TABLE && !spec_eligible(full, p->n)) return fail(MCQ_EINVAL, "MCQ_ALGO_TABLE needs 13*N <= 255 (full_3d) or 12*N <= 255 (board)");
+    if (p->algo == MCQ_ALGO_TABLE && !spec_eligible(full, p->n)) return fail(MCQ_EINVAL, "MCQ_ALGO_TABLE serves N <= 20 (full_3d) or N <= 21 (board)");
     const bool use_spec = p->algo == MCQ_ALGO_TABLE || (p->algo == MCQ_ALGO_AUTO && G == 0 && spec_eligible(full, p->n));
     if (G == 0) {
         G = 8;
@@ -737,7 +738,7 @@ int mcq_run(mcq_ctx *ctx, const mcq_run_params *p) {
             const int cells = p->n * p->n * p->n;
             if (nb.ensure((size_t)cells * sl.nbr_len * 2) || ctx->buf[B_MOVES].ensure((size_t)cells * sl.nbr_len * 2))
                 return fail(MCQ_ENOMEM, "device allocation failed (neighbour lists)");
-            build_neighbours_kernel<<<(cells + 127) / 128, 128, 0, s>>>(full, p->n, sl.nbr_len, static_cast<uint16_t *>(nb.p),
+            build_neighbours_kernel<<<(cells + 127) / 128, 128, 0, s>>>(full, p->n, sl.nbr_len, full ? 2 : 1, static_cast<uint16_t *>(nb.p),
                                                                        static_cast<uint16_t *>(ctx->buf[B_MOVES].p));
             CUDA_TRY(cudaGetLastError());
             ++launches;

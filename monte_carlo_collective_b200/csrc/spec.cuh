@@ -27,6 +27,8 @@
 // Table entries are uint8: T <= 13*N (12*N in board mode), so the kernel serves N <= 19 in
 // full_3d and N <= 21 in board mode; larger boards use anneal_kernel's line counters.
 #pragma once
+#include <type_traits>
+
 #include "anneal.cuh"
 
 namespace mcq {
@@ -57,7 +59,7 @@ __host__ __device__ inline void family_dir(int f, int &dx, int &dy, int &dz) {
 // ---- geometry tables, built once per (mode, N) and shared by every chain ----------------------
 // nbr[cell][L]: ids of all cells on the attack lines through `cell` (itself excluded), padded to a
 // multiple of 32 with the id N^3, a scratch byte at the end of every T, so updates need no predicate.
-__global__ void build_neighbours_kernel(int full, int N, int L, uint16_t *nbr, uint16_t *tmp) {
+__global__ void build_neighbours_kernel(int full, int N, int L, int esize, uint16_t *nbr, uint16_t *tmp) {
     const int cell = blockIdx.x * blockDim.x + threadIdx.x;
     if (cell >= N * N * N) return;
     const int x = cell / (N * N), y = (cell / N) % N, z = cell % N;
@@ -75,7 +77,7 @@ __global__ void build_neighbours_kernel(int full, int N, int L, uint16_t *nbr, u
         }
     }
     // Order the row so that the 32 entries one warp instruction touches fall into distinct shared-memory
-    // banks where possible (byte table: bank = (id / 4) % 32; ids in the same 4-byte word do not conflict).
+    // banks where possible (bank = (id * esize / 4) % 32; ids in the same 4-byte word do not conflict).
     // Greedy: each group of 32 takes at most one word per bank; leftovers fill the remaining slots.
     const uint16_t PAD = (uint16_t)(N * N * N), TAKEN = 0xffffu;
     int placed = 0;
@@ -85,7 +87,7 @@ __global__ void build_neighbours_kernel(int full, int N, int L, uint16_t *nbr, u
         int k = 0;
         for (int e = 0; e < n && k < 32; ++e) {
             if (list[e] == TAKEN) continue;
-            const int word = list[e] >> 2, bank = word & 31;
+            const int word = (list[e] * esize) >> 2, bank = word & 31;
             if ((banks >> bank) & 1u) { if (word_of_bank[bank] != word) continue; }
             else { banks |= 1u << bank; word_of_bank[bank] = word; }
             row[g * 32 + k++] = list[e];
@@ -166,33 +168,33 @@ __device__ __forceinline__ void sm_red_or(uint32_t addr, uint32_t bits) {
 
 // T[c] += delta for every cell c on the attack lines through one cell: its neighbour row of NR*32
 // ids starting at element `row` of nbr.  aT = shared address of the chain's table.  All lanes call.
-template <int NR>
+template <int NR, typename TE>
 __device__ __forceinline__ void table_row_add(uint32_t aT, const uint16_t *nbr, uint32_t row, int delta) {
     uint32_t c[NR];
 #pragma unroll
     for (int r = 0; r < NR; ++r) c[r] = __ldg(nbr + row + r * 32);
 #pragma unroll
     for (int r = 0; r < NR; ++r) {
-        const SmRef<unsigned char> cell{aT + c[r]};
-        cell = (unsigned char)((unsigned char)cell + delta);
+        const SmRef<TE> cell{aT + c[r] * (uint32_t)sizeof(TE)};
+        cell = (TE)((TE)cell + delta);
     }
 }
 
 // NR == 0: row length known at run time only (replay kernels); otherwise compiled in.
-template <int NR>
+template <int NR, typename TE>
 __device__ __forceinline__ void table_lines_add(uint32_t aT, const uint16_t *nbr, uint32_t row, int nr, int delta) {
     if constexpr (NR > 0) {
-        table_row_add<NR>(aT, nbr, row, delta);
+        table_row_add<NR, TE>(aT, nbr, row, delta);
     } else {
         switch (nr) {
-            case 1: table_row_add<1>(aT, nbr, row, delta); break;
-            case 2: table_row_add<2>(aT, nbr, row, delta); break;
-            case 3: table_row_add<3>(aT, nbr, row, delta); break;
-            case 4: table_row_add<4>(aT, nbr, row, delta); break;
-            case 5: table_row_add<5>(aT, nbr, row, delta); break;
-            case 6: table_row_add<6>(aT, nbr, row, delta); break;
-            case 7: table_row_add<7>(aT, nbr, row, delta); break;
-            default: table_row_add<8>(aT, nbr, row, delta); break;
+            case 1: table_row_add<1, TE>(aT, nbr, row, delta); break;
+            case 2: table_row_add<2, TE>(aT, nbr, row, delta); break;
+            case 3: table_row_add<3, TE>(aT, nbr, row, delta); break;
+            case 4: table_row_add<4, TE>(aT, nbr, row, delta); break;
+            case 5: table_row_add<5, TE>(aT, nbr, row, delta); break;
+            case 6: table_row_add<6, TE>(aT, nbr, row, delta); break;
+            case 7: table_row_add<7, TE>(aT, nbr, row, delta); break;
+            default: table_row_add<8, TE>(aT, nbr, row, delta); break;
         }
     }
 }
@@ -211,6 +213,11 @@ template <bool FULL, bool REPLAY, bool EARLY, int NR, int LPC>
 __global__ void __launch_bounds__(128, MCQ_SPEC_MINB) spec_kernel(const __grid_constant__ KArgs a) {
     constexpr unsigned FULLMASK = 0xffffffffu;
     constexpr int NF = FULL ? NFAM : NFAM - 1;
+    // full_3d: 16-bit table entries whose top bit says "a queen stands here", so the occupancy test of a
+    // candidate cell and its conflict count are one load; board mode needs no occupancy and keeps bytes
+    using TE = std::conditional_t<FULL, uint16_t, unsigned char>;
+    constexpr int OCC = FULL ? 0x8000 : 0, CNT = FULL ? 0x7fff : 0xff;
+#define TBL(base, c) (SmRef<TE>{sbase + (uint32_t)(base) + (uint32_t)(c) * (uint32_t)sizeof(TE)})
     constexpr int CPW = 32 / LPC;   // chains per warp
     constexpr unsigned LMASK = LPC == 32 ? 0xffffffffu : ((1u << LPC) - 1u);
     const int lane = threadIdx.x & 31;
@@ -232,7 +239,6 @@ __global__ void __launch_bounds__(128, MCQ_SPEC_MINB) spec_kernel(const __grid_c
 
     const int sT = a.sl.cta_bytes + (slab0 + half) * a.sl.stride;   // table T[N^3 + 1]
     const int sP = sT + a.sl.off_state;   // board: heights u8; full_3d: u32 per queen = cell id | wide id << 16
-    const int sO = sT + a.sl.off_occ;     // full_3d: occupancy bits
     const int sW = a.sl.off_wide;
     const int L = a.sl.nbr_len, rounds = a.sl.rounds;
     const uint32_t wide_bias = (uint32_t)((N - 1) * ((2 * N - 1) * (2 * N - 1) + (2 * N - 1) + 1));
@@ -240,7 +246,7 @@ __global__ void __launch_bounds__(128, MCQ_SPEC_MINB) spec_kernel(const __grid_c
     // ---- build the slabs from the external states: one chain at a time, all 32 lanes ----
     int E = 0;
     for (int h = 0; h < CPW; ++h) {
-        const int bT = a.sl.cta_bytes + (slab0 + h) * a.sl.stride, bP = bT + a.sl.off_state, bO = bT + a.sl.off_occ;
+        const int bT = a.sl.cta_bytes + (slab0 + h) * a.sl.stride, bP = bT + a.sl.off_state;
         for (int w = lane; w < a.sl.stride / 4; w += 32) SM32(bT + 4 * w) = 0u;
         __syncwarp();
         if (chain0 + h >= a.n_chains) continue;   // no chain: the slab stays zero (harmless to evaluate)
@@ -249,7 +255,6 @@ __global__ void __launch_bounds__(128, MCQ_SPEC_MINB) spec_kernel(const __grid_c
             if (FULL) {
                 const int cid = ((int)ext[3 * qi] * N + (int)ext[3 * qi + 1]) * N + (int)ext[3 * qi + 2];
                 SM32(bP + 4 * qi) = (uint32_t)cid | ((uint32_t)SM16(sW + 2 * cid) << 16);
-                sm_red_or(sbase + (uint32_t)(bO + 4 * (cid >> 5)), 1u << (cid & 31));
             } else {
                 SM8(bP + qi) = ext[qi];
             }
@@ -257,14 +262,14 @@ __global__ void __launch_bounds__(128, MCQ_SPEC_MINB) spec_kernel(const __grid_c
         __syncwarp();
         for (int qi = 0; qi < a.Q; ++qi) {
             const int c = FULL ? (int)(SM32(bP + 4 * qi) & 0xffffu) : qi * N + (int)SM8(bP + qi);
-            table_lines_add<NR>(sbase + (uint32_t)bT, a.nbr, (uint32_t)(c * L + lane), rounds, 1);
-            if (lane == 0) SM8(bT + c) = (unsigned char)(SM8(bT + c) + NF);
+            table_lines_add<NR, TE>(sbase + (uint32_t)bT, a.nbr, (uint32_t)(c * L + lane), rounds, 1);
+            if (lane == 0) TBL(bT, c) = (TE)((TE)TBL(bT, c) + NF + OCC);
             __syncwarp();
         }
         int e = 0;
         for (int qi = lane; qi < a.Q; qi += 32) {
             const int c = FULL ? (int)(SM32(bP + 4 * qi) & 0xffffu) : qi * N + (int)SM8(bP + qi);
-            e += (int)SM8(bT + c) - NF;
+            e += ((int)(TE)TBL(bT, c) & CNT) - NF;
         }
         e = __reduce_add_sync(FULLMASK, e) >> 1;   // every attacking pair was counted from both ends
         if (half == h) E = e;
@@ -328,11 +333,12 @@ __global__ void __launch_bounds__(128, MCQ_SPEC_MINB) spec_kernel(const __grid_c
                 bad = q >= (uint32_t)a.Q || i1 >= (uint32_t)N || j1 >= (uint32_t)N || k1 >= (uint32_t)N;
                 c1 = bad ? 0u : (i1 * N + j1) * N + k1;
                 if (bad) q = 0;
-                bad = bad || ((SM32(sO + 4 * (c1 >> 5)) >> (c1 & 31)) & 1u);
+                const int v1 = (int)(TE)TBL(sT, c1);
+                bad = bad || (v1 & OCC);
                 const uint32_t p0 = SM32(sP + 4 * q), w1 = SM16(sW + 2 * c1);
                 c0 = p0 & 0xffffu;
                 const uint32_t e = w1 - (p0 >> 16) + wide_bias;
-                dE = (int)SM8(sT + c1) - (int)SM8(sT + c0) + NF - (int)((SM32(4 * (e >> 5)) >> (e & 31)) & 1u);
+                dE = (v1 & CNT) - ((int)(TE)TBL(sT, c0) & CNT) + NF - (int)((SM32(4 * (e >> 5)) >> (e & 31)) & 1u);
                 aux = q | (w1 << 16);
             } else {
                 uint32_t i0 = mv & 255, j0 = (mv >> 8) & 255, k1 = (mv >> 16) & 255;
@@ -341,7 +347,7 @@ __global__ void __launch_bounds__(128, MCQ_SPEC_MINB) spec_kernel(const __grid_c
                 const uint32_t ij = i0 * N + j0, k0 = SM8(sP + ij);
                 bad = bad || (k1 == k0);
                 c0 = ij * N + k0; c1 = ij * N + k1;
-                dE = (int)SM8(sT + c1) - (int)SM8(sT + c0) + NF;
+                dE = (int)(TE)TBL(sT, c1) - (int)(TE)TBL(sT, c0) + NF;
                 aux = ij | (k1 << 16);
             }
             const double p = exp(-b64 * (double)dE);
@@ -371,13 +377,16 @@ __global__ void __launch_bounds__(128, MCQ_SPEC_MINB) spec_kernel(const __grid_c
                 // The first two candidates (words y, w) are resolved without a branch.
                 c1 = __umulhi(r.y, N3);
                 const uint32_t c1b = __umulhi(r.w, N3);
-                if ((SM32(sO + 4 * (c1 >> 5)) >> (c1 & 31)) & 1u) {
+                int v1 = (int)(TE)TBL(sT, c1);
+                if (v1 & OCC) {
                     c1 = c1b;
+                    v1 = (int)(TE)TBL(sT, c1);
                     int e = 0;
-                    while ((SM32(sO + 4 * (c1 >> 5)) >> (c1 & 31)) & 1u) {
+                    while (v1 & OCC) {
                         const Philox4 r2 = philox4x32_10((uint32_t)s, 0u, 1u + (uint32_t)(e >> 2), PHILOX_DOMAIN_STEP, key0, key1);
                         const int sel = e & 3;
                         c1 = __umulhi(sel == 0 ? r2.x : sel == 1 ? r2.y : sel == 2 ? r2.z : r2.w, N3);
+                        v1 = (int)(TE)TBL(sT, c1);
                         ++e;
                     }
                 }
@@ -385,7 +394,7 @@ __global__ void __launch_bounds__(128, MCQ_SPEC_MINB) spec_kernel(const __grid_c
                 c0 = p0 & 0xffffu;
                 const uint32_t e = w1 - (p0 >> 16) + wide_bias;
                 // the moving queen itself sits on a line through the new cell iff the cells share one
-                dE = (int)SM8(sT + c1) - (int)SM8(sT + c0) + NF - (int)((SM32(4 * (e >> 5)) >> (e & 31)) & 1u);
+                dE = (v1 & CNT) - ((int)(TE)TBL(sT, c0) & CNT) + NF - (int)((SM32(4 * (e >> 5)) >> (e & 31)) & 1u);
                 aux = q | (w1 << 16);
             } else {
                 const uint32_t ij = __umulhi(r.x, (uint32_t)(N * N));
@@ -394,7 +403,7 @@ __global__ void __launch_bounds__(128, MCQ_SPEC_MINB) spec_kernel(const __grid_c
                 uint32_t k1 = k0 + 1u + __umulhi(r.y, (uint32_t)(N - 1));
                 k1 -= (k1 >= (uint32_t)N) ? (uint32_t)N : 0u;
                 c0 = ij * N + k0; c1 = ij * N + k1;
-                dE = (int)SM8(sT + c1) - (int)SM8(sT + c0) + NF;
+                dE = (int)(TE)TBL(sT, c1) - (int)(TE)TBL(sT, c0) + NF;
                 aux = ij | (k1 << 16);
             }
             // Metropolis (experiments.py:238-239 / :326-327): u < exp(-beta dE), u = word / 2^32
@@ -474,29 +483,26 @@ __global__ void __launch_bounds__(128, MCQ_SPEC_MINB) spec_kernel(const __grid_c
                 for (int r = 0; r < NR; ++r) rb[r] = __ldg(a.nbr + bc1 * (uint32_t)L + (uint32_t)lane + r * 32);
 #pragma unroll
                 for (int r = 0; r < NR; ++r) {
-                    const SmRef<unsigned char> cell{sbase + (uint32_t)bT + ra[r]};
-                    cell = (unsigned char)((unsigned char)cell - 1);
+                    const SmRef<TE> cell{sbase + (uint32_t)bT + ra[r] * (uint32_t)sizeof(TE)};
+                    cell = (TE)((TE)cell - 1);
                 }
-                if (lane == 0) SM8(bT + bc0) = (unsigned char)(SM8(bT + bc0) - NF);
+                if (lane == 0) TBL(bT, bc0) = (TE)((TE)TBL(bT, bc0) - NF - OCC);
                 __syncwarp();
 #pragma unroll
                 for (int r = 0; r < NR; ++r) {
-                    const SmRef<unsigned char> cell{sbase + (uint32_t)bT + rb[r]};
-                    cell = (unsigned char)((unsigned char)cell + 1);
+                    const SmRef<TE> cell{sbase + (uint32_t)bT + rb[r] * (uint32_t)sizeof(TE)};
+                    cell = (TE)((TE)cell + 1);
                 }
             } else {
-                table_lines_add<NR>(sbase + (uint32_t)bT, a.nbr, bc0 * (uint32_t)L + (uint32_t)lane, rounds, -1);
-                if (lane == 0) SM8(bT + bc0) = (unsigned char)(SM8(bT + bc0) - NF);
+                table_lines_add<NR, TE>(sbase + (uint32_t)bT, a.nbr, bc0 * (uint32_t)L + (uint32_t)lane, rounds, -1);
+                if (lane == 0) TBL(bT, bc0) = (TE)((TE)TBL(bT, bc0) - NF - OCC);
                 __syncwarp();
-                table_lines_add<NR>(sbase + (uint32_t)bT, a.nbr, bc1 * (uint32_t)L + (uint32_t)lane, rounds, +1);
+                table_lines_add<NR, TE>(sbase + (uint32_t)bT, a.nbr, bc1 * (uint32_t)L + (uint32_t)lane, rounds, +1);
             }
             if (lane == 0) {
-                SM8(bT + bc1) = (unsigned char)(SM8(bT + bc1) + NF);
+                TBL(bT, bc1) = (TE)((TE)TBL(bT, bc1) + NF + OCC);
                 const int bP = bT + a.sl.off_state;
                 if (FULL) {
-                    const int bO = bT + a.sl.off_occ;
-                    SM32(bO + 4 * (bc0 >> 5)) &= ~(1u << (bc0 & 31));
-                    SM32(bO + 4 * (bc1 >> 5)) |= 1u << (bc1 & 31);
                     SM32(bP + 4 * (baux & 0xffffu)) = bc1 | (baux & 0xffff0000u);
                 } else {
                     SM8(bP + (baux & 0xffffu)) = (unsigned char)(baux >> 16);
@@ -559,6 +565,7 @@ __global__ void __launch_bounds__(128, MCQ_SPEC_MINB) spec_kernel(const __grid_c
     }
 }
 
+#undef TBL
 #undef SM8
 #undef SM16
 #undef SM32

@@ -18,9 +18,10 @@ CASES = [
     ("full_3d", 12, 60000, "random", (0.3, 3.0)),
     ("board", 15, 20000, "latin", (1.0, 4.0)),
     ("full_3d", 16, 20000, "random", (0.2, 2.0)),
-    ("full_3d", 19, 8000, "random", (0.1, 1.5)),      # largest N of the conflict-table kernel (full_3d)
+    ("full_3d", 19, 8000, "random", (0.1, 1.5)),
     ("board", 21, 8000, "random", (0.1, 1.5)),        # largest N of the conflict-table kernel (board)
-    ("full_3d", 20, 6000, "random", (0.5, 2.0)),      # line counters only
+    ("full_3d", 20, 6000, "random", (0.5, 2.0)),      # largest N of the conflict-table kernel (full_3d)
+    ("full_3d", 21, 3000, "random", (0.5, 2.0)),      # line counters only
     ("board", 33, 3000, "random", (0.5, 2.0)),
     ("board", 64, 1500, "random", (0.2, 1.0)),        # BASELINE config C5's board size
     ("full_3d", 40, 1200, "random", (0.2, 1.0)),      # 32-bit packed positions
@@ -42,7 +43,7 @@ def test_long_replay_matches_c_oracle(engine, case):
     st = _initial(mode, n, init, rng)
     betas = np.linspace(b0, b1, ns)
     g = c_oracle.generate(mode, n, st, betas, seed=int(rng.randint(1, 2 ** 31)))
-    table_ok = 13 * n <= 255 if mode == "full_3d" else 12 * n <= 255
+    table_ok = 13 * (n - 1) <= 256 if mode == "full_3d" else 12 * n <= 255
     variants = [dict(algo="lines", lanes_per_chain=8), dict(algo="lines", lanes_per_chain=32)]
     if table_ok:
         variants += [dict(algo="table"), dict(algo="table", chunk_steps=2048), dict(algo="table", lanes_per_chain=32),
