@@ -58,6 +58,7 @@ extern "C" {
 #define MCQ_ALGO_AUTO 0   /* conflict table when its uint8 entries suffice, else line counters */
 #define MCQ_ALGO_LINES 1  /* per-line occupancy counters, `lanes_per_chain` lanes per chain (anneal.cuh) */
 #define MCQ_ALGO_TABLE 2  /* per-cell conflict table, one warp per chain, speculative rounds (spec.cuh) */
+#define MCQ_ALGO_GMEM 3   /* line counters in global memory, one thread per chain: boards too large for shared memory */
 
 /* error codes */
 #define MCQ_OK 0

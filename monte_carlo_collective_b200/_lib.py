@@ -18,7 +18,7 @@ MEM_HOST, MEM_DEVICE = 0, 1
 HIST_NONE, HIST_U16, HIST_I32 = 0, 1, 2
 OK, EINVAL, ECUDA, ENOMEM, EREPLAY = 0, -1, -2, -3, -4
 ABI_VERSION = 1
-ALGO_AUTO, ALGO_LINES, ALGO_TABLE = 0, 1, 2
+ALGO_AUTO, ALGO_LINES, ALGO_TABLE, ALGO_GMEM = 0, 1, 2, 3
 
 
 class McqError(RuntimeError):

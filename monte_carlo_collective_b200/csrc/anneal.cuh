@@ -43,7 +43,10 @@ struct Layout {
     int stride;     // slab size, multiple of 16
     int pos32;      // full_3d: positions are uint32 (8-bit fields) instead of uint16 (5-bit fields)
     int pb;         // packets produced per batch = min(G, 8)
+    int off_jrn;    // G == 1: journal of state elements changed since the last best-state snapshot
 };
+
+constexpr int JRN = 62;   // journal capacity (uint16 entries); slot JRN holds the count
 
 // byte offsets inside one chain's slab for the conflict-table kernel (spec.cuh)
 struct SLayout {
@@ -97,6 +100,9 @@ struct KArgs {
     int n_bins;
     int bin_at_begin;      // bin containing t_begin
     uint32_t *acc_hist;    // [n_chains][n_bins]
+    int gslab_dummy;       // index of the dummy slab
+    unsigned char *gslab;  // line-counter kernel with G == 1: slabs live in global memory ([n_chains + 1][lay.stride],
+                           // the last one a zeroed dummy for the padding threads of the last CTA); null = shared memory
     const uint16_t *nbr;   // conflict-table kernel: neighbour lists [N^3][sl.nbr_len]
     const uint32_t *geo;   // conflict-table kernel, full_3d: shared-line bits then wide ids (sl.cta_bytes)
 };
@@ -243,7 +249,11 @@ __global__ void __launch_bounds__(256) anneal_kernel(const __grid_constant__ KAr
     const int N = a.N;
     const int PB = a.lay.pb;
 
-    unsigned char *S = smem + (size_t)cl * a.lay.stride;
+    // G == 1 with a global slab: one THREAD per chain, counters in HBM/L2 (boards too large for shared
+    // memory, e.g. N = 64: 121 KB per chain); the slab was built by gslab_build_kernel and persists
+    // between launches.
+    unsigned char *S = a.gslab ? a.gslab + (size_t)(live ? chain : a.gslab_dummy) * a.lay.stride
+                               : smem + (size_t)cl * a.lay.stride;
     uint8_t *cnt = S;
     unsigned char *st = S + a.lay.off_state;
     uint32_t *occ = reinterpret_cast<uint32_t *>(S + a.lay.off_occ);
@@ -252,7 +262,7 @@ __global__ void __launch_bounds__(256) anneal_kernel(const __grid_constant__ KAr
     const int pos32 = a.lay.pos32;
 
     const uint8_t *ext = a.state + (size_t)(live ? chain : 0) * a.state_bytes;
-    int E = build_chain<G>(a, S, ext, live, g);
+    int E = a.gslab ? (live ? a.cur_e[chain] : 0) : build_chain<G>(a, S, ext, live, g);
 
     LaneLines<G> L;
     L.init(a, g);
@@ -418,6 +428,14 @@ __global__ void __launch_bounds__(256) anneal_kernel(const __grid_constant__ KAr
             E += dE;
             ++n_acc;
             accbits |= 1u << (t & 31);
+            if constexpr (G == 1) {
+                // one thread per chain: copying the whole state at every new best would dominate, so the
+                // elements touched since the last snapshot are journalled and only those are copied
+                uint16_t *jrn = reinterpret_cast<uint16_t *>(S + a.lay.off_jrn);
+                const int jn = jrn[JRN];
+                if (jn < JRN) jrn[jn] = (uint16_t)(FULL ? qsel : i0 * N + j0);
+                if (jn <= JRN) jrn[JRN] = (uint16_t)(jn + 1);   // JRN + 1 = overflow: next snapshot is a full copy
+            }
         }
         __syncwarp();
         bool improved = accept && (E < best);
@@ -431,14 +449,35 @@ __global__ void __launch_bounds__(256) anneal_kernel(const __grid_constant__ KAr
             if (!stop_now) best_step = t + 1;
             // snapshot: the state at the first visit of the minimum (strict <, :252 / :340)
             uint8_t *bs = a.best_state + (size_t)chain * a.state_bytes;
-            if constexpr (FULL) {
-                for (int qi = g; qi < a.Q; qi += G) {
-                    int i, j, k;
-                    unpack_pos(pos32, load_pos(st, pos32, qi), i, j, k);
-                    bs[3 * qi] = (uint8_t)i; bs[3 * qi + 1] = (uint8_t)j; bs[3 * qi + 2] = (uint8_t)k;
+            bool full_copy = true;
+            if constexpr (G == 1) {
+                uint16_t *jrn = reinterpret_cast<uint16_t *>(S + a.lay.off_jrn);
+                const int jn = jrn[JRN];
+                if (jn <= JRN) {
+                    full_copy = false;
+                    for (int e = 0; e < jn; ++e) {
+                        const int el = jrn[e];
+                        if constexpr (FULL) {
+                            int i, j, k;
+                            unpack_pos(pos32, load_pos(st, pos32, el), i, j, k);
+                            bs[3 * el] = (uint8_t)i; bs[3 * el + 1] = (uint8_t)j; bs[3 * el + 2] = (uint8_t)k;
+                        } else {
+                            bs[el] = st[el];
+                        }
+                    }
                 }
-            } else {
-                for (int c = g; c < a.Q; c += G) bs[c] = st[c];
+                jrn[JRN] = 0;
+            }
+            if (full_copy) {
+                if constexpr (FULL) {
+                    for (int qi = g; qi < a.Q; qi += G) {
+                        int i, j, k;
+                        unpack_pos(pos32, load_pos(st, pos32, qi), i, j, k);
+                        bs[3 * qi] = (uint8_t)i; bs[3 * qi + 1] = (uint8_t)j; bs[3 * qi + 2] = (uint8_t)k;
+                    }
+                } else {
+                    for (int c = g; c < a.Q; c += G) bs[c] = st[c];
+                }
             }
         }
         if (stop_now) {
@@ -474,14 +513,16 @@ __global__ void __launch_bounds__(256) anneal_kernel(const __grid_constant__ KAr
             a.acc_hist[(size_t)chain * a.n_bins + bin] = (uint32_t)(n_acc - bin_mark);
         }
         uint8_t *out = a.state + (size_t)chain * a.state_bytes;
-        if constexpr (FULL) {
-            for (int qi = g; qi < a.Q; qi += G) {
-                int i, j, k;
-                unpack_pos(pos32, load_pos(st, pos32, qi), i, j, k);
-                out[3 * qi] = (uint8_t)i; out[3 * qi + 1] = (uint8_t)j; out[3 * qi + 2] = (uint8_t)k;
+        if (!a.gslab || a.t_end == a.n_steps) {   // a global slab keeps the state between launches
+            if constexpr (FULL) {
+                for (int qi = g; qi < a.Q; qi += G) {
+                    int i, j, k;
+                    unpack_pos(pos32, load_pos(st, pos32, qi), i, j, k);
+                    out[3 * qi] = (uint8_t)i; out[3 * qi + 1] = (uint8_t)j; out[3 * qi + 2] = (uint8_t)k;
+                }
+            } else {
+                for (int c = g; c < a.Q; c += G) out[c] = st[c];
             }
-        } else {
-            for (int c = g; c < a.Q; c += G) out[c] = st[c];
         }
         if (g == 0) {
             a.cur_e[chain] = E;
@@ -493,6 +534,17 @@ __global__ void __launch_bounds__(256) anneal_kernel(const __grid_constant__ KAr
             a.steps_done[chain] = done;
             if (REPLAY && a.near_cnt) a.near_cnt[chain] += near;
         }
+    }
+}
+
+// Builds the global-memory slabs (counters, packed state, occupancy) and the initial energies: one warp per chain.
+__global__ void __launch_bounds__(32) gslab_build_kernel(const __grid_constant__ KArgs a) {
+    const int chain = a.chain_begin + blockIdx.x;
+    if (chain >= a.n_chains) return;
+    const int e = build_chain<32>(a, a.gslab + (size_t)chain * a.lay.stride, a.state + (size_t)chain * a.state_bytes, true, threadIdx.x);
+    if (threadIdx.x == 0) {
+        a.cur_e[chain] = e;
+        reinterpret_cast<uint16_t *>(a.gslab + (size_t)chain * a.lay.stride + a.lay.off_jrn)[JRN] = 0;   // empty journal
     }
 }
 

@@ -84,7 +84,8 @@ static Layout make_layout(int full, int N, int Q, int G) {
     L.off_pkt = round_up(L.off_occ + occ_b, 16);
     L.pb = G < 8 ? G : 8;
     L.off_hst = L.off_pkt + L.pb * PKT_BYTES;
-    L.stride = round_up(L.off_hst + HBLK * 4, 16);
+    L.off_jrn = L.off_hst + HBLK * 4;
+    L.stride = round_up(L.off_jrn + (G == 1 ? (JRN + 2) * 2 : 0), 16);
     return L;
 }
 
@@ -110,6 +111,10 @@ static SLayout make_spec_layout(int full, int N, int Q) {
 // board: uint8 entries hold at most 12*N; full_3d: uint16 entries, bounded by the neighbour-row length
 // the kernels are compiled for (13*(N-1) <= 256) and the 16-bit cell / wide ids
 static inline bool spec_eligible(int full, int N) { return full ? 13 * (N - 1) <= 256 : 12 * N <= 255; }
+
+#ifndef MCQ_GMEM_MIN_CHAINS_PER_SM
+#define MCQ_GMEM_MIN_CHAINS_PER_SM 8   // below this many shared-memory chains per SM the global-memory kernel takes over
+#endif
 
 static inline int state_bytes_of(int mode, int n, int q) { return mode == MCQ_MODE_FULL3D ? 3 * q : n * n; }
 
@@ -322,7 +327,7 @@ struct DevBuf {
 
 enum BufId {
     B_SEEDS, B_GROUP, B_BETA, B_INIT, B_RMOVES, B_RUNIF, B_STATE, B_BEST, B_REC, B_OCC, B_HIST0, B_HIST1,
-    B_ABITS, B_ACCH, B_BINS, B_STATE_IN, B_MOVES, B_OUT, B_SUME, B_SUME2, B_NBUF
+    B_ABITS, B_ACCH, B_BINS, B_STATE_IN, B_MOVES, B_OUT, B_SUME, B_SUME2, B_GSLAB, B_NBUF
 };
 
 }  // namespace mcq
@@ -392,6 +397,7 @@ static cudaError_t launch_spec(int lpc, const KArgs &a, bool replay, int grid, i
 
 static cudaError_t launch_anneal(int G, const KArgs &a, bool replay, int grid, int block, size_t smem, cudaStream_t s) {
     switch (G) {
+        case 1: return launch_g<1>(a, replay, grid, block, smem, s);
         case 4: return launch_g<4>(a, replay, grid, block, smem, s);
         case 8: return launch_g<8>(a, replay, grid, block, smem, s);
         case 16: return launch_g<16>(a, replay, grid, block, smem, s);
@@ -637,19 +643,24 @@ int mcq_run(mcq_ctx *ctx, const mcq_run_params *p) {
     const size_t smem_sm = ctx->prop.sharedMemPerMultiprocessor;
     int G = p->lanes_per_chain;
     if (G != 0 && G != 4 && G != 8 && G != 16 && G != 32) return fail(MCQ_EINVAL, "lanes_per_chain must be 0, 4, 8, 16 or 32");
-    if (p->algo < MCQ_ALGO_AUTO || p->algo > MCQ_ALGO_TABLE) return fail(MCQ_EINVAL, "unknown algo");
+    if (p->algo < MCQ_ALGO_AUTO || p->algo > MCQ_ALGO_GMEM) return fail(MCQ_EINVAL, "unknown algo");
     if (p->algo == MCQ_ALGO_TABLE && !spec_eligible(full, p->n)) return fail(MCQ_EINVAL, "MCQ_ALGO_TABLE serves N <= 20 (full_3d) or N <= 21 (board)");
     const bool use_spec = p->algo == MCQ_ALGO_TABLE || (p->algo == MCQ_ALGO_AUTO && G == 0 && spec_eligible(full, p->n));
+    // Boards whose line counters leave room for only a few chains per SM run one thread per chain with the
+    // counters in global memory (HBM-bound byte traffic instead of a latency-bound handful of warps).
+    const bool use_gmem = !use_spec && (p->algo == MCQ_ALGO_GMEM ||
+        (p->algo == MCQ_ALGO_AUTO && G == 0 && (size_t)make_layout(full, p->n, p->q, 32).stride * MCQ_GMEM_MIN_CHAINS_PER_SM > smem_sm));
+    if (use_gmem) G = 1;
     if (G == 0) {
         G = 8;
         while (G < 32 && (size_t)make_layout(full, p->n, p->q, G).stride * (32 / G) > smem_block) G *= 2;
     }
     Layout lay = make_layout(full, p->n, p->q, G);
-    if ((size_t)lay.stride * (32 / G) > smem_block) return fail(MCQ_ENOMEM, "a warp's chains do not fit in shared memory; raise lanes_per_chain");
+    if (!use_gmem && (size_t)lay.stride * (32 / G) > smem_block) return fail(MCQ_ENOMEM, "a warp's chains do not fit in shared memory; raise lanes_per_chain");
     int wpc = p->warps_per_cta;
     if (wpc < 0 || wpc > 8) return fail(MCQ_EINVAL, "warps_per_cta must be in [0, 8]");
     int best_w = 1, best_chains = 0, best_ctas = 1;
-    for (int w = 8; w >= 1; --w) {
+    for (int w = 8; w >= 1 && !use_gmem; --w) {
         if (wpc && w != wpc) continue;
         const int cpc_w = w * 32 / G;
         const size_t need = (size_t)cpc_w * lay.stride;
@@ -658,11 +669,11 @@ int mcq_run(mcq_ctx *ctx, const mcq_run_params *p) {
         ctas = std::min(ctas, 64 / w);
         if (ctas * cpc_w > best_chains) { best_chains = ctas * cpc_w; best_w = w; best_ctas = ctas; }
     }
-    if (best_chains == 0) return fail(MCQ_ENOMEM, "requested warps_per_cta does not fit in shared memory");
-    int cpc = best_w * 32 / G;
-    int block = best_w * 32;
+    if (best_chains == 0 && !use_gmem) return fail(MCQ_ENOMEM, "requested warps_per_cta does not fit in shared memory");
+    int cpc = use_gmem ? 128 : best_w * 32 / G;
+    int block = use_gmem ? 128 : best_w * 32;
     int grid = (nc + cpc - 1) / cpc;
-    size_t smem = (size_t)cpc * lay.stride;
+    size_t smem = use_gmem ? 0 : (size_t)cpc * lay.stride;
     const SLayout sl = make_spec_layout(full, p->n, p->q);
     int spec_lpc = 32;
     if (use_spec) {
@@ -708,7 +719,7 @@ int mcq_run(mcq_ctx *ctx, const mcq_run_params *p) {
         if (getenv("MCQ_DEBUG"))
             fprintf(stderr, "[mcq] table kernel: lanes/chain %d, %d warps/CTA, %d CTAs/SM (max %d), grid %d, smem %zu B, score %.3f\n",
                     spec_lpc, w, best_ctas_spec, max_ctas(spec_lpc), grid, smem, best_score);
-    } else {   // cap residency (explicit limit, or balance the waves) by padding the shared-memory request
+    } else if (!use_gmem) {   // cap residency (explicit limit, or balance the waves) by padding the shared-memory request
         int ctas = best_ctas;
         const int sms = ctx->prop.multiProcessorCount;
         if (p->max_chains_per_sm > 0) ctas = std::max(1, std::min(ctas, p->max_chains_per_sm / cpc));
@@ -801,6 +812,16 @@ int mcq_run(mcq_ctx *ctx, const mcq_run_params *p) {
         ++launches;
     }
     CUDA_TRY(cudaMemcpyAsync(a.best_state, a.state, (size_t)nc * sbytes, cudaMemcpyDeviceToDevice, s));
+    if (use_gmem) {   // slabs in global memory: built once, reused by every launch of this call
+        if (ctx->buf[B_GSLAB].ensure(((size_t)nc + 1) * lay.stride)) return fail(MCQ_ENOMEM, "device allocation failed (global-memory slabs)");
+        a.gslab = static_cast<unsigned char *>(ctx->buf[B_GSLAB].p);
+        a.gslab_dummy = nc;
+        CUDA_TRY(cudaMemsetAsync(a.gslab + (size_t)nc * lay.stride, 0, lay.stride, s));
+        a.chain_begin = 0;
+        gslab_build_kernel<<<nc, 32, 0, s>>>(a);
+        CUDA_TRY(cudaGetLastError());
+        ++launches;
+    }
 
     // ---- acceptance bins ----
     a.n_bins = p->n_bins;

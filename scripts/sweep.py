@@ -97,3 +97,9 @@ if which == "tail":
         os.environ["MCQ_STREAMS"] = st
         for nc in (4736 * 4, 20480, 4736 * 5, 4736 * 4 + 148 * 4):
             run("tail" + st, "full_3d", 12, nc, 100000, algo="table", lanes_per_chain=32)
+
+if which == "bign":
+    for mode, n, nc, ns in (("board", 64, 1184, 20000), ("board", 64, 16384, 20000), ("board", 64, 65536, 5000), ("board", 33, 8192, 20000),
+                            ("board", 24, 8192, 20000), ("full_3d", 24, 8192, 20000), ("full_3d", 40, 4096, 10000)):
+        for algo in ("lines", "gmem"):
+            run("bign", mode, n, nc, ns, algo=algo)

@@ -44,7 +44,8 @@ def test_long_replay_matches_c_oracle(engine, case):
     betas = np.linspace(b0, b1, ns)
     g = c_oracle.generate(mode, n, st, betas, seed=int(rng.randint(1, 2 ** 31)))
     table_ok = 13 * (n - 1) <= 256 if mode == "full_3d" else 12 * n <= 255
-    variants = [dict(algo="lines", lanes_per_chain=8), dict(algo="lines", lanes_per_chain=32)]
+    variants = [dict(algo="lines", lanes_per_chain=8), dict(algo="lines", lanes_per_chain=32), dict(algo="gmem"),
+                dict(algo="gmem", chunk_steps=512)]
     if table_ok:
         variants += [dict(algo="table"), dict(algo="table", chunk_steps=2048), dict(algo="table", lanes_per_chain=32),
                      dict(algo="table", lanes_per_chain=16)]
@@ -80,6 +81,7 @@ def test_early_stop_replay_matches_c_oracle(engine, patience):
     free = c_oracle.generate("board", n, st, betas, seed=99)
     want = c_oracle.replay("board", n, st, free["moves"], free["uniforms"], betas, patience=patience)
     for kw in (dict(algo="table"), dict(algo="lines"), dict(algo="table", chunk_steps=32), dict(algo="lines", chunk_steps=96),
+               dict(algo="gmem"), dict(algo="gmem", chunk_steps=64),
                dict(algo="table", lanes_per_chain=32), dict(algo="table", lanes_per_chain=16)):
         r = engine.run("board", n, ns, np.array([1], dtype=np.uint64), betas, init_states=st[None].astype(np.uint8),
                        history="full", hist_dtype=np.int32, accept_bits=True, early_stop_patience=patience,

@@ -60,7 +60,7 @@ def test_same_seed_same_chain_any_layout(engine, mode):
                dict(algo="table", warps_per_cta=1), dict(algo="table", chunk_steps=96, warps_per_cta=2),
                dict(algo="table", lanes_per_chain=32), dict(algo="table", lanes_per_chain=16, warps_per_cta=3),
                dict(algo="table", lanes_per_chain=32, chunk_steps=64), dict(algo="table", lanes_per_chain=16, chunk_steps=64),
-               dict(algo="lines", chunk_steps=320, warps_per_cta=3)):
+               dict(algo="lines", chunk_steps=320, warps_per_cta=3), dict(algo="gmem"), dict(algo="gmem", chunk_steps=160)):
         r = engine.run(mode, n, ns, seeds, betas, history="full", accept_bits=True, **kw)
         assert (r.energy_history == base.energy_history).all(), kw
         assert (r.best_state == base.best_state).all(), kw
@@ -141,6 +141,7 @@ def test_early_stop_board(engine):
     stop = engine.run("board", n, ns, seeds, betas, history="full", accept_bits=True, early_stop_patience=300, n_bins=100)
     assert (stop.steps_done < ns).any()
     for kw in (dict(algo="lines"), dict(algo="lines", lanes_per_chain=32, chunk_steps=128), dict(algo="table", chunk_steps=64),
+               dict(algo="gmem"), dict(algo="gmem", chunk_steps=96),
                dict(algo="table", lanes_per_chain=32), dict(algo="table", lanes_per_chain=16, chunk_steps=160)):
         other = engine.run("board", n, ns, seeds, betas, history="full", accept_bits=True, early_stop_patience=300,
                            n_bins=100, **kw)
