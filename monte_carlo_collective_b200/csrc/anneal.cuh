@@ -310,7 +310,22 @@ __global__ void __launch_bounds__(256) anneal_kernel(const __grid_constant__ KAr
 
     for (int t = a.t_begin; t < a.t_end; ++t) {
         // ---------------- packet production (once per PB steps) ----------------
-        if (((t - a.t_begin) & (PB - 1)) == 0) {
+        // (a single lane per chain keeps its step's words in registers: no staging)
+        uint4 w1 = make_uint4(0u, 0u, 0u, 0u);
+        uint32_t w1_4 = 0u;
+        if constexpr (G == 1) {
+            const int ts = min(t, a.t_end - 1);
+            if constexpr (REPLAY) {
+                const double u = un_row[ts], b = beta64_row[ts];
+                w1 = make_uint4(mv_row[ts], (uint32_t)__double2loint(u), (uint32_t)__double2hiint(u), (uint32_t)__double2loint(b));
+                w1_4 = (uint32_t)__double2hiint(b);
+            } else {
+                const Philox4 r = philox4x32_10((uint32_t)ts, 0u, 0u, PHILOX_DOMAIN_STEP, k0, k1);
+                w1 = make_uint4(r.x, r.y, r.z, r.w);
+                w1_4 = __float_as_uint(c_pref);                       // fetched one step ahead
+                if (live && ts + 1 < a.t_end) c_pref = __ldg(beta_row + ts + 1);
+            }
+        } else if (((t - a.t_begin) & (PB - 1)) == 0) {
             __syncwarp();
             if (g < PB) {
                 const int ts = t + g;
@@ -341,8 +356,8 @@ __global__ void __launch_bounds__(256) anneal_kernel(const __grid_constant__ KAr
         }
 
         const unsigned char *pk = pkt + ((t - a.t_begin) & (PB - 1)) * PKT_BYTES;
-        const uint4 w = *reinterpret_cast<const uint4 *>(pk);
-        const uint32_t w4 = reinterpret_cast<const uint32_t *>(pk)[4];
+        const uint4 w = G == 1 ? w1 : *reinterpret_cast<const uint4 *>(pk);
+        const uint32_t w4 = G == 1 ? w1_4 : reinterpret_cast<const uint32_t *>(pk)[4];
 
         // ---------------- proposal ----------------
         int i0, j0, k0c, i1, j1, k1c, qsel = 0, cid1 = 0;
@@ -485,7 +500,7 @@ __global__ void __launch_bounds__(256) anneal_kernel(const __grid_constant__ KAr
             done = t;
             if (g == 0 && a.acc_hist) a.acc_hist[(size_t)chain * a.n_bins + bin] = (uint32_t)(n_acc - bin_mark);
         }
-        if (active && g == 0) hst[t & (HBLK - 1)] = E;
+        if (active && g == 0 && (a.hist_kind || G > 1)) hst[t & (HBLK - 1)] = E;
 
         // ---------------- history flush ----------------
         if ((t & (HBLK - 1)) == HBLK - 1 || t == a.t_end - 1) {

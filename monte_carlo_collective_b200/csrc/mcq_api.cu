@@ -23,6 +23,7 @@
 namespace mcq {
 
 static thread_local std::string g_err;
+static int g_smem_optin = 227 * 1024;   // sharedMemPerBlockOptin of the device (set by mcq_create)
 
 static int fail(int code, const std::string &msg) {
     g_err = msg;
@@ -348,7 +349,9 @@ namespace mcq {
 template <int G, bool FULL, bool REPLAY>
 static cudaError_t launch_one(const KArgs &a, int grid, int block, size_t smem, cudaStream_t s) {
     auto k = anneal_kernel<G, FULL, REPLAY>;
-    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    // always the device maximum: the attribute is per function and per device, so concurrent host threads
+    // (one engine each) must not race different values into it
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin);
     if (e != cudaSuccess) return e;
     k<<<grid, block, smem, s>>>(a);
     return cudaGetLastError();
@@ -363,7 +366,9 @@ static cudaError_t launch_g(const KArgs &a, bool replay, int grid, int block, si
 template <bool FULL, bool REPLAY, bool EARLY, int NR, int LPC>
 static cudaError_t launch_spec_one(const KArgs &a, int grid, int block, size_t smem, cudaStream_t s) {
     auto k = spec_kernel<FULL, REPLAY, EARLY, NR, LPC>;
-    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    // always the device maximum: the attribute is per function and per device, so concurrent host threads
+    // (one engine each) must not race different values into it
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin);
     if (e != cudaSuccess) return e;
     k<<<grid, block, smem, s>>>(a);
     return cudaGetLastError();
@@ -480,6 +485,7 @@ int mcq_create(int device, mcq_ctx **out) {
         delete c;
         return fail(MCQ_ECUDA, "libmcq is built for sm_100a (B200) only; this device is older");
     }
+    g_smem_optin = (int)c->prop.sharedMemPerBlockOptin;
     CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     for (auto &ss : c->sub_stream) CUDA_TRY(cudaStreamCreateWithFlags(&ss, cudaStreamNonBlocking));
@@ -574,7 +580,7 @@ int mcq_energy(mcq_ctx *ctx, int mode, int n, int q, int n_states, const uint8_t
         if (ctx->buf[B_OUT].ensure((size_t)n_states * 4)) return fail(MCQ_ENOMEM, "device allocation failed");
         d_out = static_cast<int *>(ctx->buf[B_OUT].p);
     }
-    CUDA_TRY(cudaFuncSetAttribute(energy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, a.lay.stride));
+    CUDA_TRY(cudaFuncSetAttribute(energy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin));
     energy_kernel<<<n_states, 32, a.lay.stride, s>>>(a, d_out);
     CUDA_TRY(cudaGetLastError());
     if (mem == MCQ_MEM_HOST) CUDA_TRY(cudaMemcpyAsync(out_energy, d_out, (size_t)n_states * 4, cudaMemcpyDeviceToHost, s));
@@ -597,7 +603,7 @@ int mcq_delta_energy(mcq_ctx *ctx, int mode, int n, int q, int n_states, const u
         if (ctx->buf[B_OUT].ensure(cnt * 4)) return fail(MCQ_ENOMEM, "device allocation failed");
         d_out = static_cast<int *>(ctx->buf[B_OUT].p);
     }
-    CUDA_TRY(cudaFuncSetAttribute(delta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, a.lay.stride));
+    CUDA_TRY(cudaFuncSetAttribute(delta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin));
     delta_kernel<<<n_states, 32, a.lay.stride, s>>>(a, n_moves, static_cast<const uint32_t *>(d_moves), d_out);
     CUDA_TRY(cudaGetLastError());
     if (mem == MCQ_MEM_HOST) CUDA_TRY(cudaMemcpyAsync(out_delta, d_out, cnt * 4, cudaMemcpyDeviceToHost, s));

@@ -103,3 +103,7 @@ if which == "bign":
                             ("board", 24, 8192, 20000), ("full_3d", 24, 8192, 20000), ("full_3d", 40, 4096, 10000)):
         for algo in ("lines", "gmem"):
             run("bign", mode, n, nc, ns, algo=algo)
+
+if which == "gm":
+    for mode, n, nc, ns in (("board", 64, 16384, 20000), ("board", 64, 65536, 5000), ("board", 33, 8192, 20000), ("full_3d", 40, 4096, 10000)):
+        run("gm", mode, n, nc, ns, algo="gmem")

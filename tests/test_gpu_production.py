@@ -196,3 +196,28 @@ def test_argument_errors(engine):
     r = engine.run("full_3d", 4, 10, s, b, q=10)          # Q != N^2 is legal with random init
     assert r.final_state.shape == (2, 10, 3)
     assert engine.run("board", 4, 10, np.zeros(0, dtype=np.uint64), b).n_chains == 0
+
+
+def test_engines_in_concurrent_host_threads(engine):
+    """Independent problems issued from several host threads (one engine each, as drivers.measure_min_energy_vs_N
+    does) must not disturb each other: same results as the sequential runs."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    import monte_carlo_collective_b200 as mcq
+    ns = 4000
+    betas = schedules.beta_table(LIN, ns)
+    jobs = [("board", n) for n in (5, 9, 12, 13, 14, 21, 24)] + [("full_3d", n) for n in (4, 8, 12, 13, 20, 22)]
+    seeds = np.arange(96, dtype=np.uint64) + 9
+    want = {j: engine.run(j[0], j[1], ns, seeds, betas, history="none") for j in jobs}
+    engines = {}
+
+    def work(job):
+        import threading
+        eng = engines.setdefault(threading.get_ident(), mcq.Engine(0))
+        r = eng.run(job[0], job[1], ns, seeds, betas, history="none")
+        return job, r
+
+    for _ in range(2):
+        with ThreadPoolExecutor(max_workers=6) as ex:
+            for job, r in ex.map(work, jobs * 2):
+                assert (r.best_energy == want[job].best_energy).all() and (r.final_state == want[job].final_state).all(), job
