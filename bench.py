@@ -303,14 +303,15 @@ def main():
 
     # ---- roofline of the dominant kernel (spec_kernel<FULL>), DESIGN.md section 4 ----
     # Bound: SM issue slots (4 warp-instructions / clk / SM).  Algorithmic warp-instructions per proposal of
-    # the speculative mapping: a round of 32 lanes costs 117 (+70 when it commits an accepted move) and
-    # retires adv(p) = (1-(1-p)^32)/p proposals at acceptance probability p.
+    # the speculative mapping: a round of 32 lanes costs 54 and retires
+    # adv(p) = (1-(1-p)^32)/p proposals at acceptance probability p; the random words of a step cost
+    # 64/32 (one Philox4x32-10 call + ring store per lane per 32 consumed steps); an accepted move costs 70.
     kernel_pps = nc * ns * args.steps / (kernel_ms * 1e-3)        # this rank's kernel-only rate (CUDA events in mcq_run)
     f_mhz = clk["sm_mhz"] or 1965.0
     peak = ISSUE_PER_CLK_PER_SM * eng.sm_count * f_mhz * 1e6
     p_acc = max(acc_rate, 1e-6)
     p_round = 1.0 - (1.0 - p_acc) ** 32
-    i_alg = (117.0 + 70.0 * p_round) * p_acc / p_round
+    i_alg = 54.0 * p_acc / p_round + 2.0 + 70.0 * p_acc
     achieved = kernel_pps * i_alg
     peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
     hbm_peak = json.load(open(peaks_file))["hbm_gbs"] if os.path.isfile(peaks_file) else 6650.0
@@ -318,7 +319,7 @@ def main():
         "bound": "issue", "achieved": achieved / 1e9, "peak": peak / 1e9, "unit": "Gwarp-inst/s",
         "frac": achieved / peak, "traffic": AS_BUILT["dram_bytes_per_launch"],
         "kernel": "spec_kernel<FULL=1,REPLAY=0,EARLY=0>", "i_alg_warp_inst_per_proposal": i_alg,
-        "i_alg_formula": "(117 + 70*(1-(1-p)^32)) * p / (1-(1-p)^32), p = measured acceptance rate",
+        "i_alg_formula": "54/adv(p) + 2 + 70*p, adv(p) = (1-(1-p)^32)/p, p = measured acceptance rate",
         "kernel_proposals_per_s": kernel_pps, "sm_clock_mhz_used": f_mhz, "sm_count": eng.sm_count,
         "as_built": AS_BUILT,
         "frac_under_survey_mapping": kernel_pps * I_ALG["full_3d"] / peak,
