@@ -60,6 +60,7 @@ struct SLayout {
     int rounds;     // nbr_len / 32
     int off_wide;   // CTA-shared geometry (full_3d): [lut bits | wide ids]; byte offset of the wide ids
     int cta_bytes;  // bytes of CTA-shared geometry in front of the slabs (0 in board mode)
+    int wide_bias;  // (N-1)*(W^2+W+1), W = 2N-1
 };
 
 struct KArgs {

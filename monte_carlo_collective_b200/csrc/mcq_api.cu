@@ -104,6 +104,7 @@ static SLayout make_spec_layout(int full, int N, int Q) {
     L.rounds = L.nbr_len / 32;
     const int W = 2 * N - 1;
     const int lut_bytes = (W * W * W + 31) / 32 * 4;
+    L.wide_bias = (N - 1) * (W * W + W + 1);
     L.off_wide = full ? lut_bytes : 0;
     L.cta_bytes = full ? round_up(lut_bytes + N * N * N * 2, 16) : 0;
     return L;

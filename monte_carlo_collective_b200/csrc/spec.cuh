@@ -148,6 +148,19 @@ struct SmRef {
         else asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
         return (T)v;
     }
+    // stores take the low bits of a 32-bit register: no masking needed (st.shared.u8/u16 truncate)
+    __device__ __forceinline__ void put(uint32_t v) const {
+        if constexpr (sizeof(T) == 1) asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+        else if constexpr (sizeof(T) == 2) asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+        else asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+    }
+    __device__ __forceinline__ uint32_t get() const {
+        uint32_t v;
+        if constexpr (sizeof(T) == 1) asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+        else if constexpr (sizeof(T) == 2) asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr));
+        else asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+        return v;
+    }
     __device__ __forceinline__ const SmRef &operator=(T x) const {
         const uint32_t v = (uint32_t)x;
         if constexpr (sizeof(T) == 1) asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
@@ -176,7 +189,7 @@ __device__ __forceinline__ void table_row_add(uint32_t aT, const uint16_t *nbr, 
 #pragma unroll
     for (int r = 0; r < NR; ++r) {
         const SmRef<TE> cell{aT + c[r] * (uint32_t)sizeof(TE)};
-        cell = (TE)((TE)cell + delta);
+        cell.put(cell.get() + (uint32_t)delta);
     }
 }
 
@@ -220,9 +233,11 @@ __global__ void __launch_bounds__(128, MCQ_SPEC_MINB) spec_kernel(const __grid_c
 #define TBL(base, c) (SmRef<TE>{sbase + (uint32_t)(base) + (uint32_t)(c) * (uint32_t)sizeof(TE)})
     constexpr int CPW = 32 / LPC;   // chains per warp
     constexpr unsigned LMASK = LPC == 32 ? 0xffffffffu : ((1u << LPC) - 1u);
-    const int lane = threadIdx.x & 31;
+    int lane = threadIdx.x & 31;
+    uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem);
+    // keep both in registers: the compiler otherwise re-derives them (S2R + address-window arithmetic) every round
+    asm volatile("" : "+r"(lane), "+r"(sbase));
     const int sub = lane & (LPC - 1), half = lane / LPC;
-    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem);
     const int N = a.N;
 
     // ---- CTA-shared geometry: shared-line bits at offset 0, cell -> wide id at sl.off_wide ----
@@ -241,7 +256,7 @@ __global__ void __launch_bounds__(128, MCQ_SPEC_MINB) spec_kernel(const __grid_c
     const int sP = sT + a.sl.off_state;   // board: heights u8; full_3d: u32 per queen = cell id | wide id << 16
     const int sW = a.sl.off_wide;
     const int L = a.sl.nbr_len, rounds = a.sl.rounds;
-    const uint32_t wide_bias = (uint32_t)((N - 1) * ((2 * N - 1) * (2 * N - 1) + (2 * N - 1) + 1));
+    const uint32_t wide_bias = (uint32_t)a.sl.wide_bias;   // (N-1)*(W^2+W+1): centres the wide-id difference in the LUT
 
     // ---- build the slabs from the external states: one chain at a time, all 32 lanes ----
     int E = 0;
@@ -484,23 +499,23 @@ __global__ void __launch_bounds__(128, MCQ_SPEC_MINB) spec_kernel(const __grid_c
 #pragma unroll
                 for (int r = 0; r < NR; ++r) {
                     const SmRef<TE> cell{sbase + (uint32_t)bT + ra[r] * (uint32_t)sizeof(TE)};
-                    cell = (TE)((TE)cell - 1);
+                    cell.put(cell.get() - 1u);
                 }
-                if (lane == 0) TBL(bT, bc0) = (TE)((TE)TBL(bT, bc0) - NF - OCC);
+                if (lane == 0) TBL(bT, bc0).put(TBL(bT, bc0).get() - (uint32_t)(NF + OCC));
                 __syncwarp();
 #pragma unroll
                 for (int r = 0; r < NR; ++r) {
                     const SmRef<TE> cell{sbase + (uint32_t)bT + rb[r] * (uint32_t)sizeof(TE)};
-                    cell = (TE)((TE)cell + 1);
+                    cell.put(cell.get() + 1u);
                 }
             } else {
                 table_lines_add<NR, TE>(sbase + (uint32_t)bT, a.nbr, bc0 * (uint32_t)L + (uint32_t)lane, rounds, -1);
-                if (lane == 0) TBL(bT, bc0) = (TE)((TE)TBL(bT, bc0) - NF - OCC);
+                if (lane == 0) TBL(bT, bc0).put(TBL(bT, bc0).get() - (uint32_t)(NF + OCC));
                 __syncwarp();
                 table_lines_add<NR, TE>(sbase + (uint32_t)bT, a.nbr, bc1 * (uint32_t)L + (uint32_t)lane, rounds, +1);
             }
             if (lane == 0) {
-                TBL(bT, bc1) = (TE)((TE)TBL(bT, bc1) + NF + OCC);
+                TBL(bT, bc1).put(TBL(bT, bc1).get() + (uint32_t)(NF + OCC));
                 const int bP = bT + a.sl.off_state;
                 if (FULL) {
                     SM32(bP + 4 * (baux & 0xffffu)) = bc1 | (baux & 0xffff0000u);
