@@ -60,8 +60,10 @@ static int make_coefs(int full, int N, int4 coef[NFAM]) {
     coef[0] = make_int4(N, 1, 0, base[0]);
     coef[1] = make_int4(N, 0, 1, base[1]);
     coef[2] = make_int4(0, N, 1, base[2]);
-    coef[3] = make_int4(1, -1, W, base[3] + o);
-    coef[4] = make_int4(1, 1, W, base[4]);
+    // k is the fastest index in every family that depends on it: a board move changes k only, so the old and
+    // the new cell's counters of a family are at most N-1 bytes apart (same line / sector in the global-memory variant)
+    coef[3] = make_int4(N, -N, 1, base[3] + o * N);   // (i-j+o)*N + k
+    coef[4] = make_int4(N, N, 1, base[4]);            // (i+j)*N + k
     coef[5] = make_int4(1, W, -1, base[5] + o);
     coef[6] = make_int4(1, W, 1, base[6]);
     coef[7] = make_int4(W, 1, -1, base[7] + o);

@@ -107,3 +107,6 @@ if which == "bign":
 if which == "gm":
     for mode, n, nc, ns in (("board", 64, 16384, 20000), ("board", 64, 65536, 5000), ("board", 33, 8192, 20000), ("full_3d", 40, 4096, 10000)):
         run("gm", mode, n, nc, ns, algo="gmem")
+
+if which == "gmprof":
+    run("gmprof", "board", 64, 16384, 3000, algo="gmem")
