@@ -380,8 +380,9 @@ __global__ void __launch_bounds__(256) anneal_kernel(const __grid_constant__ KAr
                     if (!live || !((occ[cid1 >> 5] >> (cid1 & 31)) & 1u)) break;
                     // occupied (the queen's own cell counts, experiments.py:230): redraw
                     if (tries == 0) word = w.w;
+                    else if (tries == 1) word = w.x * (uint32_t)a.Q;   // what the queen draw left of word x
                     else {
-                        const int e = tries - 1;
+                        const int e = tries - 2;
                         const Philox4 r = philox4x32_10((uint32_t)t, 0u, 1u + (uint32_t)(e >> 2), PHILOX_DOMAIN_STEP, k0, k1);
                         const int s = e & 3;
                         word = s == 0 ? r.x : s == 1 ? r.y : s == 2 ? r.z : r.w;

@@ -212,6 +212,14 @@ __device__ __forceinline__ void table_lines_add(uint32_t aT, const uint16_t *nbr
     }
 }
 
+// base + idx * scale as ONE 64-bit multiply-add (the compiler otherwise widens, shifts and adds with carries)
+template <typename T>
+__device__ __forceinline__ T *ptr_mad(T *base, uint32_t idx, uint32_t scale) {
+    uint64_t r;
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(r) : "r"(idx), "r"(scale), "l"((uint64_t)base));
+    return reinterpret_cast<T *>(r);
+}
+
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -237,7 +245,7 @@ __global__ void __launch_bounds__(128, MCQ_SPEC_MINB) spec_kernel(const __grid_c
     uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem);
     // keep both in registers: the compiler otherwise re-derives them (S2R + address-window arithmetic) every round
     asm volatile("" : "+r"(lane), "+r"(sbase));
-    const int sub = lane & (LPC - 1), half = lane / LPC;
+    const int sub = lane & (LPC - 1), half = LPC == 32 ? 0 : lane / LPC;
     const int N = a.N;
 
     // ---- CTA-shared geometry: shared-line bits at offset 0, cell -> wide id at sl.off_wide ----
@@ -326,6 +334,7 @@ __global__ void __launch_bounds__(128, MCQ_SPEC_MINB) spec_kernel(const __grid_c
     // history row, addressed by history index h = step + 1 (h_origin = index held by column 0)
     unsigned char *hrow = static_cast<unsigned char *>(a.hist) +
                           ((long long)chain_c * a.hist_pitch - a.h_origin) * (a.hist_kind == 1 ? 2 : 4);
+    const uint16_t *nbr_lane = a.nbr + lane;   // this lane's column of the neighbour rows
     uint32_t *abits_row = a.abits ? a.abits + (size_t)chain_c * a.abits_pitch : nullptr;
 
     while (CPW == 1 ? t < a.t_end : __any_sync(FULLMASK, t < a.t_end)) {
@@ -369,7 +378,7 @@ __global__ void __launch_bounds__(128, MCQ_SPEC_MINB) spec_kernel(const __grid_c
             accept = !bad && u64 < fmin(1.0, p);
             near_flag = !bad && fabs(u64 - p) < 1e-6;
         } else {
-            const float cb = __ldg(beta_row + s);
+            const float cb = __ldg(ptr_mad(beta_row, (uint32_t)s, 4u));
             // Random words of step s come from a 64-step ring in the slab: a round consumes only the
             // steps it commits, so one Philox4x32-10 call per lane refills LPC steps that are all used,
             // instead of recomputing the discarded lanes' words every round.
@@ -396,13 +405,19 @@ __global__ void __launch_bounds__(128, MCQ_SPEC_MINB) spec_kernel(const __grid_c
                 if (v1 & OCC) {
                     c1 = c1b;
                     v1 = (int)(TE)TBL(sT, c1);
-                    int e = 0;
-                    while (v1 & OCC) {
-                        const Philox4 r2 = philox4x32_10((uint32_t)s, 0u, 1u + (uint32_t)(e >> 2), PHILOX_DOMAIN_STEP, key0, key1);
-                        const int sel = e & 3;
-                        c1 = __umulhi(sel == 0 ? r2.x : sel == 1 ? r2.y : sel == 2 ? r2.z : r2.w, N3);
+                    if (v1 & OCC) {
+                        // third candidate: what is left of word x after the queen draw (its next mixed-radix
+                        // digit), so that only (Q/N^3)^3 of the proposals pay for another Philox call
+                        c1 = __umulhi(r.x * (uint32_t)a.Q, N3);
                         v1 = (int)(TE)TBL(sT, c1);
-                        ++e;
+                        int e = 0;
+                        while (v1 & OCC) {
+                            const Philox4 r2 = philox4x32_10((uint32_t)s, 0u, 1u + (uint32_t)(e >> 2), PHILOX_DOMAIN_STEP, key0, key1);
+                            const int sel = e & 3;
+                            c1 = __umulhi(sel == 0 ? r2.x : sel == 1 ? r2.y : sel == 2 ? r2.z : r2.w, N3);
+                            v1 = (int)(TE)TBL(sT, c1);
+                            ++e;
+                        }
                     }
                 }
                 const uint32_t w1 = SM16(sW + 2 * c1);
@@ -462,8 +477,8 @@ __global__ void __launch_bounds__(128, MCQ_SPEC_MINB) spec_kernel(const __grid_c
         // history: steps t .. t+adv_h-1; all but an accepted last one keep the old energy
         if (sub < adv_h && a.hist_kind) {
             const int v = (sub == first) ? E_new : E;
-            if (a.hist_kind == 1) reinterpret_cast<uint16_t *>(hrow)[s + 1] = (uint16_t)v;
-            else reinterpret_cast<int *>(hrow)[s + 1] = v;
+            if (a.hist_kind == 1) *reinterpret_cast<uint16_t *>(ptr_mad(hrow + 2, (uint32_t)s, 2u)) = (uint16_t)v;
+            else *reinterpret_cast<int *>(ptr_mad(hrow + 4, (uint32_t)s, 4u)) = v;
         }
         // acceptance bins: close every bin that ends at or before the last consumed step
         if (active) {
@@ -493,9 +508,9 @@ __global__ void __launch_bounds__(128, MCQ_SPEC_MINB) spec_kernel(const __grid_c
                 // both neighbour rows are fetched before the first phase so that only one L2 round trip is exposed
                 uint32_t ra[NR], rb[NR];
 #pragma unroll
-                for (int r = 0; r < NR; ++r) ra[r] = __ldg(a.nbr + bc0 * (uint32_t)L + (uint32_t)lane + r * 32);
+                for (int r = 0; r < NR; ++r) ra[r] = __ldg(ptr_mad(nbr_lane, bc0, 2u * (uint32_t)L) + r * 32);
 #pragma unroll
-                for (int r = 0; r < NR; ++r) rb[r] = __ldg(a.nbr + bc1 * (uint32_t)L + (uint32_t)lane + r * 32);
+                for (int r = 0; r < NR; ++r) rb[r] = __ldg(ptr_mad(nbr_lane, bc1, 2u * (uint32_t)L) + r * 32);
 #pragma unroll
                 for (int r = 0; r < NR; ++r) {
                     const SmRef<TE> cell{sbase + (uint32_t)bT + ra[r] * (uint32_t)sizeof(TE)};
