@@ -102,7 +102,7 @@ static SLayout make_spec_layout(int full, int N, int Q) {
     L.off_rec = L.off_occ + occ_b;
     L.off_ring = round_up(L.off_rec + 8 * 4, 16);
     L.stride = L.off_ring + 64 * 16;
-    L.nbr_len = round_up((full ? NFAM : NFAM - 1) * (N - 1), 32);
+    L.nbr_len = round_up((full ? NFAM : NFAM - 1) * (N - 1) + 1, 32);   // the cell itself + its line neighbours
     L.rounds = L.nbr_len / 32;
     const int W = 2 * N - 1;
     const int lut_bytes = (W * W * W + 31) / 32 * 4;
@@ -114,7 +114,7 @@ static SLayout make_spec_layout(int full, int N, int Q) {
 
 // board: uint8 entries hold at most 12*N; full_3d: uint16 entries, bounded by the neighbour-row length
 // the kernels are compiled for (13*(N-1) <= 256) and the 16-bit cell / wide ids
-static inline bool spec_eligible(int full, int N) { return full ? 13 * (N - 1) <= 256 : 12 * N <= 255; }
+static inline bool spec_eligible(int full, int N) { return full ? 13 * (N - 1) + 1 <= 256 : 12 * N <= 255; }
 
 #ifndef MCQ_GMEM_MIN_CHAINS_PER_SM
 #define MCQ_GMEM_MIN_CHAINS_PER_SM 8   // below this many shared-memory chains per SM the global-memory kernel takes over

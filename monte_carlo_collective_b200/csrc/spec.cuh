@@ -10,15 +10,18 @@
 //     discarded lanes in the next round with the same counter-based Philox words (the random
 //     numbers of step s depend on (seed, s) only).  With ~3 % acceptance a round retires ~21
 //     proposals.
-//   * delta-E is two byte loads: the slab holds T[cell] = sum over the 13 (12 in board mode)
-//     attack lines through `cell` of the number of queens on that line, i.e. exactly what
-//     conflicts_for_queen / conflicts_for_position (mcmc.py:185-226, mcmc_board.py:147-193) count,
-//     plus 13 (12) for a queen standing on the cell itself:
-//         conflicts(old) = T[old] - 13,   conflicts(new) = T[new] - [old and new share a line]
+//   * delta-E is two table loads: the slab holds T[cell] = number of queens on the 13 (12 in board mode)
+//     attack lines through `cell`, a queen standing on the cell itself counted once -- for an empty
+//     cell exactly what conflicts_for_position counts, for a queen's cell conflicts_for_queen + 1
+//     (mcmc.py:185-226, mcmc_board.py:147-193):
+//         conflicts(old) = T[old] - 1,   conflicts(new) = T[new] - [old and new share a line]
 //     "old and new share a line" depends on the coordinate differences only and is one bit of a
-//     (2N-1)^3-bit table.  T is maintained on accept only: -1 on every cell of the 13 lines
-//     through the old cell, +1 on those through the new one; the cell lists are rows of a
-//     neighbour table shared by all chains (geometry only, L2-resident), 32 cells per warp load.
+//     (2N-1)^3-bit table.  T is maintained on accept only: -1 on the old cell and every cell of the
+//     lines through it, +1 on the new one and its lines; the cell lists are rows of a neighbour
+//     table shared by all chains (geometry only, L2-resident), 32 cells per warp load.  In full_3d
+//     bit 15 of an entry says "a queen stands here" (the occupancy test of a candidate cell and its
+//     conflict count are one load); it is flipped by the same read-modify-write that counts the
+//     queen herself, because slot 0 of every row is the cell itself.
 //   * cells are handled as linear ids c = (i*N+j)*N+k throughout; coordinates are only
 //     reconstructed when a state leaves the kernel.
 //   * per-chain shared memory is ~N^3 + 4*Q bytes (2.6 KB at N=12), so the register file, not
@@ -57,8 +60,9 @@ __host__ __device__ inline void family_dir(int f, int &dx, int &dy, int &dz) {
 }
 
 // ---- geometry tables, built once per (mode, N) and shared by every chain ----------------------
-// nbr[cell][L]: ids of all cells on the attack lines through `cell` (itself excluded), padded to a
-// multiple of 32 with the id N^3, a scratch byte at the end of every T, so updates need no predicate.
+// nbr[cell][L]: slot 0 = `cell` itself, then the ids of all other cells on the attack lines through it,
+// padded to a multiple of 32 with the id N^3, a scratch entry at the end of every T, so updates need
+// no predicate.  (Lane 0 therefore always handles the moved queen's own cell in its first entry.)
 __global__ void build_neighbours_kernel(int full, int N, int L, int esize, uint16_t *nbr, uint16_t *tmp) {
     const int cell = blockIdx.x * blockDim.x + threadIdx.x;
     if (cell >= N * N * N) return;
@@ -85,6 +89,11 @@ __global__ void build_neighbours_kernel(int full, int N, int L, int esize, uint1
         unsigned banks = 0u;
         int word_of_bank[32];
         int k = 0;
+        if (g == 0) {
+            const int word = (cell * esize) >> 2;
+            banks = 1u << (word & 31); word_of_bank[word & 31] = word;
+            row[k++] = (uint16_t)cell;
+        }
         for (int e = 0; e < n && k < 32; ++e) {
             if (list[e] == TAKEN) continue;
             const int word = (list[e] * esize) >> 2, bank = word & 31;
@@ -178,36 +187,39 @@ __device__ __forceinline__ void sm_red_or(uint32_t addr, uint32_t bits) {
 #define SM8(off) (SmRef<unsigned char>{sbase + (uint32_t)(off)})
 #define SM16(off) (SmRef<uint16_t>{sbase + (uint32_t)(off)})
 #define SM32(off) (SmRef<uint32_t>{sbase + (uint32_t)(off)})
+#define SM8X(addr) (SmRef<unsigned char>{(uint32_t)(addr)})    // absolute shared-window address
+#define SM32X(addr) (SmRef<uint32_t>{(uint32_t)(addr)})
 
-// T[c] += delta for every cell c on the attack lines through one cell: its neighbour row of NR*32
-// ids starting at element `row` of nbr.  aT = shared address of the chain's table.  All lanes call.
+// T[c] += delta for every entry of one neighbour row (NR*32 ids, this lane's column starting at `row`);
+// the row's first entry of lane 0 is the cell itself and takes delta0 instead (its own weight and, in
+// full_3d, the occupied flag).  aT = shared address of the chain's table.  All lanes call.
 template <int NR, typename TE>
-__device__ __forceinline__ void table_row_add(uint32_t aT, const uint16_t *nbr, uint32_t row, int delta) {
+__device__ __forceinline__ void table_row_add(uint32_t aT, const uint16_t *row, uint32_t delta, uint32_t delta0) {
     uint32_t c[NR];
 #pragma unroll
-    for (int r = 0; r < NR; ++r) c[r] = __ldg(nbr + row + r * 32);
+    for (int r = 0; r < NR; ++r) c[r] = __ldg(row + r * 32);
 #pragma unroll
     for (int r = 0; r < NR; ++r) {
         const SmRef<TE> cell{aT + c[r] * (uint32_t)sizeof(TE)};
-        cell.put(cell.get() + (uint32_t)delta);
+        cell.put(cell.get() + (r == 0 ? delta0 : delta));
     }
 }
 
 // NR == 0: row length known at run time only (replay kernels); otherwise compiled in.
 template <int NR, typename TE>
-__device__ __forceinline__ void table_lines_add(uint32_t aT, const uint16_t *nbr, uint32_t row, int nr, int delta) {
+__device__ __forceinline__ void table_lines_add(uint32_t aT, const uint16_t *row, int nr, uint32_t delta, uint32_t delta0) {
     if constexpr (NR > 0) {
-        table_row_add<NR, TE>(aT, nbr, row, delta);
+        table_row_add<NR, TE>(aT, row, delta, delta0);
     } else {
         switch (nr) {
-            case 1: table_row_add<1, TE>(aT, nbr, row, delta); break;
-            case 2: table_row_add<2, TE>(aT, nbr, row, delta); break;
-            case 3: table_row_add<3, TE>(aT, nbr, row, delta); break;
-            case 4: table_row_add<4, TE>(aT, nbr, row, delta); break;
-            case 5: table_row_add<5, TE>(aT, nbr, row, delta); break;
-            case 6: table_row_add<6, TE>(aT, nbr, row, delta); break;
-            case 7: table_row_add<7, TE>(aT, nbr, row, delta); break;
-            default: table_row_add<8, TE>(aT, nbr, row, delta); break;
+            case 1: table_row_add<1, TE>(aT, row, delta, delta0); break;
+            case 2: table_row_add<2, TE>(aT, row, delta, delta0); break;
+            case 3: table_row_add<3, TE>(aT, row, delta, delta0); break;
+            case 4: table_row_add<4, TE>(aT, row, delta, delta0); break;
+            case 5: table_row_add<5, TE>(aT, row, delta, delta0); break;
+            case 6: table_row_add<6, TE>(aT, row, delta, delta0); break;
+            case 7: table_row_add<7, TE>(aT, row, delta, delta0); break;
+            default: table_row_add<8, TE>(aT, row, delta, delta0); break;
         }
     }
 }
@@ -266,6 +278,11 @@ __global__ void __launch_bounds__(128, MCQ_SPEC_MINB) spec_kernel(const __grid_c
     const int L = a.sl.nbr_len, rounds = a.sl.rounds;
     const uint32_t wide_bias = (uint32_t)a.sl.wide_bias;   // (N-1)*(W^2+W+1): centres the wide-id difference in the LUT
 
+    const uint16_t *nbr_lane = a.nbr + lane;   // this lane's column of the neighbour rows
+    // what a queen adds to the entry of her own cell (slot 0 of the cell's row, i.e. lane 0's first entry):
+    // herself once, and the occupied flag; every other entry of the row changes by one
+    const uint32_t d0 = lane == 0 ? 1u + (uint32_t)OCC : 1u;
+
     // ---- build the slabs from the external states: one chain at a time, all 32 lanes ----
     int E = 0;
     for (int h = 0; h < CPW; ++h) {
@@ -285,14 +302,13 @@ __global__ void __launch_bounds__(128, MCQ_SPEC_MINB) spec_kernel(const __grid_c
         __syncwarp();
         for (int qi = 0; qi < a.Q; ++qi) {
             const int c = FULL ? (int)(SM32(bP + 4 * qi) & 0xffffu) : qi * N + (int)SM8(bP + qi);
-            table_lines_add<NR, TE>(sbase + (uint32_t)bT, a.nbr, (uint32_t)(c * L + lane), rounds, 1);
-            if (lane == 0) TBL(bT, c) = (TE)((TE)TBL(bT, c) + NF + OCC);
+            table_lines_add<NR, TE>(sbase + (uint32_t)bT, ptr_mad(nbr_lane, (uint32_t)c, 2u * (uint32_t)L), rounds, 1u, d0);
             __syncwarp();
         }
         int e = 0;
         for (int qi = lane; qi < a.Q; qi += 32) {
             const int c = FULL ? (int)(SM32(bP + 4 * qi) & 0xffffu) : qi * N + (int)SM8(bP + qi);
-            e += ((int)(TE)TBL(bT, c) & CNT) - NF;
+            e += ((int)(TE)TBL(bT, c) & CNT) - 1;
         }
         e = __reduce_add_sync(FULLMASK, e) >> 1;   // every attacking pair was counted from both ends
         if (half == h) E = e;
@@ -334,7 +350,6 @@ __global__ void __launch_bounds__(128, MCQ_SPEC_MINB) spec_kernel(const __grid_c
     // history row, addressed by history index h = step + 1 (h_origin = index held by column 0)
     unsigned char *hrow = static_cast<unsigned char *>(a.hist) +
                           ((long long)chain_c * a.hist_pitch - a.h_origin) * (a.hist_kind == 1 ? 2 : 4);
-    const uint16_t *nbr_lane = a.nbr + lane;   // this lane's column of the neighbour rows
     uint32_t *abits_row = a.abits ? a.abits + (size_t)chain_c * a.abits_pitch : nullptr;
 
     while (CPW == 1 ? t < a.t_end : __any_sync(FULLMASK, t < a.t_end)) {
@@ -362,7 +377,7 @@ __global__ void __launch_bounds__(128, MCQ_SPEC_MINB) spec_kernel(const __grid_c
                 const uint32_t p0 = SM32(sP + 4 * q), w1 = SM16(sW + 2 * c1);
                 c0 = p0 & 0xffffu;
                 const uint32_t e = w1 - (p0 >> 16) + wide_bias;
-                dE = (v1 & CNT) - ((int)(TE)TBL(sT, c0) & CNT) + NF - (int)((SM32(4 * (e >> 5)) >> (e & 31)) & 1u);
+                dE = (v1 & CNT) - ((int)(TE)TBL(sT, c0) & CNT) + 1 - (int)((SM32(4 * (e >> 5)) >> (e & 31)) & 1u);
                 aux = q | (w1 << 16);
             } else {
                 uint32_t i0 = mv & 255, j0 = (mv >> 8) & 255, k1 = (mv >> 16) & 255;
@@ -371,7 +386,7 @@ __global__ void __launch_bounds__(128, MCQ_SPEC_MINB) spec_kernel(const __grid_c
                 const uint32_t ij = i0 * N + j0, k0 = SM8(sP + ij);
                 bad = bad || (k1 == k0);
                 c0 = ij * N + k0; c1 = ij * N + k1;
-                dE = (int)(TE)TBL(sT, c1) - (int)(TE)TBL(sT, c0) + NF;
+                dE = (int)(TE)TBL(sT, c1) - (int)(TE)TBL(sT, c0) + 1;
                 aux = ij | (k1 << 16);
             }
             const double p = exp(-b64 * (double)dE);
@@ -424,7 +439,7 @@ __global__ void __launch_bounds__(128, MCQ_SPEC_MINB) spec_kernel(const __grid_c
                 c0 = p0 & 0xffffu;
                 const uint32_t e = w1 - (p0 >> 16) + wide_bias;
                 // the moving queen itself sits on a line through the new cell iff the cells share one
-                dE = (v1 & CNT) - ((int)(TE)TBL(sT, c0) & CNT) + NF - (int)((SM32(4 * (e >> 5)) >> (e & 31)) & 1u);
+                dE = (v1 & CNT) - ((int)(TE)TBL(sT, c0) & CNT) + 1 - (int)((SM32(4 * (e >> 5)) >> (e & 31)) & 1u);
                 aux = q | (w1 << 16);
             } else {
                 const uint32_t ij = __umulhi(r.x, (uint32_t)(N * N));
@@ -433,7 +448,7 @@ __global__ void __launch_bounds__(128, MCQ_SPEC_MINB) spec_kernel(const __grid_c
                 uint32_t k1 = k0 + 1u + __umulhi(r.y, (uint32_t)(N - 1));
                 k1 -= (k1 >= (uint32_t)N) ? (uint32_t)N : 0u;
                 c0 = ij * N + k0; c1 = ij * N + k1;
-                dE = (int)(TE)TBL(sT, c1) - (int)(TE)TBL(sT, c0) + NF;
+                dE = (int)(TE)TBL(sT, c1) - (int)(TE)TBL(sT, c0) + 1;
                 aux = ij | (k1 << 16);
             }
             // Metropolis (experiments.py:238-239 / :326-327): u < exp(-beta dE), u = word / 2^32
@@ -504,6 +519,7 @@ __global__ void __launch_bounds__(128, MCQ_SPEC_MINB) spec_kernel(const __grid_c
                 bc0 = __shfl_sync(FULLMASK, wc0, hl); bc1 = __shfl_sync(FULLMASK, wc1, hl); baux = __shfl_sync(FULLMASK, waux, hl);
                 bT = a.sl.cta_bytes + (slab0 + hl / LPC) * a.sl.stride;
             }
+            const uint32_t aT = sbase + (uint32_t)bT;
             if constexpr (NR > 0) {
                 // both neighbour rows are fetched before the first phase so that only one L2 round trip is exposed
                 uint32_t ra[NR], rb[NR];
@@ -513,29 +529,27 @@ __global__ void __launch_bounds__(128, MCQ_SPEC_MINB) spec_kernel(const __grid_c
                 for (int r = 0; r < NR; ++r) rb[r] = __ldg(ptr_mad(nbr_lane, bc1, 2u * (uint32_t)L) + r * 32);
 #pragma unroll
                 for (int r = 0; r < NR; ++r) {
-                    const SmRef<TE> cell{sbase + (uint32_t)bT + ra[r] * (uint32_t)sizeof(TE)};
-                    cell.put(cell.get() - 1u);
+                    const SmRef<TE> cell{aT + ra[r] * (uint32_t)sizeof(TE)};
+                    cell.put(cell.get() - (r == 0 ? d0 : 1u));
                 }
-                if (lane == 0) TBL(bT, bc0).put(TBL(bT, bc0).get() - (uint32_t)(NF + OCC));
                 __syncwarp();
 #pragma unroll
                 for (int r = 0; r < NR; ++r) {
-                    const SmRef<TE> cell{sbase + (uint32_t)bT + rb[r] * (uint32_t)sizeof(TE)};
-                    cell.put(cell.get() + 1u);
+                    const SmRef<TE> cell{aT + rb[r] * (uint32_t)sizeof(TE)};
+                    cell.put(cell.get() + (r == 0 ? d0 : 1u));
                 }
             } else {
-                table_lines_add<NR, TE>(sbase + (uint32_t)bT, a.nbr, bc0 * (uint32_t)L + (uint32_t)lane, rounds, -1);
-                if (lane == 0) TBL(bT, bc0).put(TBL(bT, bc0).get() - (uint32_t)(NF + OCC));
+                table_lines_add<NR, TE>(aT, ptr_mad(nbr_lane, bc0, 2u * (uint32_t)L), rounds, 0u - 1u, 0u - d0);
                 __syncwarp();
-                table_lines_add<NR, TE>(sbase + (uint32_t)bT, a.nbr, bc1 * (uint32_t)L + (uint32_t)lane, rounds, +1);
+                table_lines_add<NR, TE>(aT, ptr_mad(nbr_lane, bc1, 2u * (uint32_t)L), rounds, 1u, d0);
             }
-            if (lane == 0) {
-                TBL(bT, bc1).put(TBL(bT, bc1).get() + (uint32_t)(NF + OCC));
-                const int bP = bT + a.sl.off_state;
+            // the moved queen's new position (lane 0 only; a predicated store, not a branch)
+            {
+                const uint32_t aP = aT + (uint32_t)a.sl.off_state;
                 if (FULL) {
-                    SM32(bP + 4 * (baux & 0xffffu)) = bc1 | (baux & 0xffff0000u);
+                    if (lane == 0) SM32X(aP + 4 * (baux & 0xffffu)).put(bc1 | (baux & 0xffff0000u));
                 } else {
-                    SM8(bP + (baux & 0xffffu)) = (unsigned char)(baux >> 16);
+                    if (lane == 0) SM8X(aP + (baux & 0xffffu)).put(baux >> 16);
                 }
             }
             __syncwarp();
@@ -599,5 +613,7 @@ __global__ void __launch_bounds__(128, MCQ_SPEC_MINB) spec_kernel(const __grid_c
 #undef SM8
 #undef SM16
 #undef SM32
+#undef SM8X
+#undef SM32X
 
 }  // namespace mcq
