@@ -417,22 +417,20 @@ __global__ void __launch_bounds__(128, MCQ_SPEC_MINB) spec_kernel(const __grid_c
                 c1 = __umulhi(r.y, N3);
                 const uint32_t c1b = __umulhi(r.w, N3);
                 int v1 = (int)(TE)TBL(sT, c1);
+                const int v1b = (int)(TE)TBL(sT, c1b);
+                if (v1 & OCC) { c1 = c1b; v1 = v1b; }   // two selects
                 if (v1 & OCC) {
-                    c1 = c1b;
+                    // third candidate: what is left of word x after the queen draw (its next mixed-radix
+                    // digit), so that only (Q/N^3)^3 of the proposals pay for another Philox call
+                    c1 = __umulhi(r.x * (uint32_t)a.Q, N3);
                     v1 = (int)(TE)TBL(sT, c1);
-                    if (v1 & OCC) {
-                        // third candidate: what is left of word x after the queen draw (its next mixed-radix
-                        // digit), so that only (Q/N^3)^3 of the proposals pay for another Philox call
-                        c1 = __umulhi(r.x * (uint32_t)a.Q, N3);
+                    int e = 0;
+                    while (v1 & OCC) {
+                        const Philox4 r2 = philox4x32_10((uint32_t)s, 0u, 1u + (uint32_t)(e >> 2), PHILOX_DOMAIN_STEP, key0, key1);
+                        const int sel = e & 3;
+                        c1 = __umulhi(sel == 0 ? r2.x : sel == 1 ? r2.y : sel == 2 ? r2.z : r2.w, N3);
                         v1 = (int)(TE)TBL(sT, c1);
-                        int e = 0;
-                        while (v1 & OCC) {
-                            const Philox4 r2 = philox4x32_10((uint32_t)s, 0u, 1u + (uint32_t)(e >> 2), PHILOX_DOMAIN_STEP, key0, key1);
-                            const int sel = e & 3;
-                            c1 = __umulhi(sel == 0 ? r2.x : sel == 1 ? r2.y : sel == 2 ? r2.z : r2.w, N3);
-                            v1 = (int)(TE)TBL(sT, c1);
-                            ++e;
-                        }
+                        ++e;
                     }
                 }
                 const uint32_t w1 = SM16(sW + 2 * c1);
@@ -490,19 +488,14 @@ __global__ void __launch_bounds__(128, MCQ_SPEC_MINB) spec_kernel(const __grid_c
             if (badm && sub == 0) atomicAdd(a.replay_err, (unsigned)__popc(badm));
         }
         // history: steps t .. t+adv_h-1; all but an accepted last one keep the old energy
-        if (sub < adv_h && a.hist_kind) {
+        // (two predicated stores rather than a branch)
+        {
+            const bool wr = sub < adv_h;
             const int v = (sub == first) ? E_new : E;
-            if (a.hist_kind == 1) *reinterpret_cast<uint16_t *>(ptr_mad(hrow + 2, (uint32_t)s, 2u)) = (uint16_t)v;
-            else *reinterpret_cast<int *>(ptr_mad(hrow + 4, (uint32_t)s, 4u)) = v;
-        }
-        // acceptance bins: close every bin that ends at or before the last consumed step
-        if (active) {
-            while (t + adv - 1 >= next_edge) {
-                if (sub == 0 && a.acc_hist) a.acc_hist[(size_t)chain * a.n_bins + bin] = (uint32_t)(n_acc - bin_mark);
-                bin_mark = n_acc;
-                ++bin;
-                next_edge = a.bin_starts[bin + 1];
-            }
+            uint16_t *h16 = reinterpret_cast<uint16_t *>(ptr_mad(hrow + 2, (uint32_t)s, 2u));
+            int *h32 = reinterpret_cast<int *>(ptr_mad(hrow + 4, (uint32_t)s, 4u));
+            if (wr && a.hist_kind == 1) *h16 = (uint16_t)v;
+            if (wr && a.hist_kind == 2) *h32 = v;
         }
         // ---------------- apply the committed moves: whole warp, one chain after the other ----------------
         const bool has = first >= 0;
@@ -527,17 +520,18 @@ __global__ void __launch_bounds__(128, MCQ_SPEC_MINB) spec_kernel(const __grid_c
                 for (int r = 0; r < NR; ++r) ra[r] = __ldg(ptr_mad(nbr_lane, bc0, 2u * (uint32_t)L) + r * 32);
 #pragma unroll
                 for (int r = 0; r < NR; ++r) rb[r] = __ldg(ptr_mad(nbr_lane, bc1, 2u * (uint32_t)L) + r * 32);
+                // the entries of one row are distinct cells (pads share a scratch entry nobody reads), so all
+                // loads of a phase are issued before its stores: one shared-memory round trip per phase, not NR
+                uint32_t va[NR];
 #pragma unroll
-                for (int r = 0; r < NR; ++r) {
-                    const SmRef<TE> cell{aT + ra[r] * (uint32_t)sizeof(TE)};
-                    cell.put(cell.get() - (r == 0 ? d0 : 1u));
-                }
+                for (int r = 0; r < NR; ++r) { ra[r] = aT + ra[r] * (uint32_t)sizeof(TE); va[r] = SmRef<TE>{ra[r]}.get(); }
+#pragma unroll
+                for (int r = 0; r < NR; ++r) SmRef<TE>{ra[r]}.put(va[r] - (r == 0 ? d0 : 1u));
                 __syncwarp();
 #pragma unroll
-                for (int r = 0; r < NR; ++r) {
-                    const SmRef<TE> cell{aT + rb[r] * (uint32_t)sizeof(TE)};
-                    cell.put(cell.get() + (r == 0 ? d0 : 1u));
-                }
+                for (int r = 0; r < NR; ++r) { rb[r] = aT + rb[r] * (uint32_t)sizeof(TE); va[r] = SmRef<TE>{rb[r]}.get(); }
+#pragma unroll
+                for (int r = 0; r < NR; ++r) SmRef<TE>{rb[r]}.put(va[r] + (r == 0 ? d0 : 1u));
             } else {
                 table_lines_add<NR, TE>(aT, ptr_mad(nbr_lane, bc0, 2u * (uint32_t)L), rounds, 0u - 1u, 0u - d0);
                 __syncwarp();
@@ -554,33 +548,43 @@ __global__ void __launch_bounds__(128, MCQ_SPEC_MINB) spec_kernel(const __grid_c
             }
             __syncwarp();
         }
-        if (has) {
-            const int ta = t + first;
-            E = E_new;
-            ++n_acc;
-            if (sub == 0 && abits_row) atomicOr(abits_row + (ta >> 5), 1u << (ta & 31));
-            if (improved) {
-                // snapshot: the state at the first visit of the minimum (strict <, :252 / :340)
-                best = E;
-                if (!stop) best_step = ta + 1;
-                uint8_t *bs = a.best_state + (size_t)chain * a.state_bytes;
-                if (FULL) {
-                    for (int qi = sub; qi < a.Q; qi += LPC) {
-                        const int c = (int)(SM32(sP + 4 * qi) & 0xffffu);
-                        bs[3 * qi] = (uint8_t)(c / (N * N)); bs[3 * qi + 1] = (uint8_t)((c / N) % N); bs[3 * qi + 2] = (uint8_t)(c % N);
+        // ---------------- bookkeeping; everything infrequent sits behind ONE branch ----------------
+        const int n_before = n_acc;
+        if (has) { E = E_new; ++n_acc; }
+        const bool edge = active && t + adv - 1 >= next_edge;
+        if (edge || improved || stop || (has && abits_row != nullptr)) {
+            // acceptance bins: close every bin that ends at or before the last consumed step (an accept
+            // of this round belongs to the bin its step lies in, i.e. the one that stays open)
+            while (active && t + adv - 1 >= next_edge) {
+                if (sub == 0 && a.acc_hist) a.acc_hist[(size_t)chain * a.n_bins + bin] = (uint32_t)(n_before - bin_mark);
+                bin_mark = n_before;
+                ++bin;
+                next_edge = a.bin_starts[bin + 1];
+            }
+            if (has) {
+                const int ta = t + first;
+                if (sub == 0 && abits_row) atomicOr(abits_row + (ta >> 5), 1u << (ta & 31));
+                if (improved) {
+                    // snapshot: the state at the first visit of the minimum (strict <, :252 / :340)
+                    best = E;
+                    if (!stop) best_step = ta + 1;
+                    uint8_t *bs = a.best_state + (size_t)chain * a.state_bytes;
+                    if (FULL) {
+                        for (int qi = sub; qi < a.Q; qi += LPC) {
+                            const int c = (int)(SM32(sP + 4 * qi) & 0xffffu);
+                            bs[3 * qi] = (uint8_t)(c / (N * N)); bs[3 * qi + 1] = (uint8_t)((c / N) % N); bs[3 * qi + 2] = (uint8_t)(c % N);
+                        }
+                    } else {
+                        for (int c = sub; c < a.Q; c += LPC) bs[c] = SM8(sP + c);
                     }
-                } else {
-                    for (int c = sub; c < a.Q; c += LPC) bs[c] = SM8(sP + c);
                 }
             }
+            if (stop) {
+                done = t + adv - 1;
+                if (sub == 0 && a.acc_hist) a.acc_hist[(size_t)chain * a.n_bins + bin] = (uint32_t)(n_acc - bin_mark);
+            }
         }
-        if (stop) {
-            done = t + adv - 1;
-            if (sub == 0 && a.acc_hist) a.acc_hist[(size_t)chain * a.n_bins + bin] = (uint32_t)(n_acc - bin_mark);
-            t = a.t_end;   // this chain is finished; the other groups of the warp go on
-        } else {
-            t += adv;
-        }
+        t = stop ? a.t_end : t + adv;   // a stopped chain is finished; the other groups of the warp go on
     }
 
     // ---------------- write the record back ----------------
