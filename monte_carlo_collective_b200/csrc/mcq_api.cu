@@ -696,7 +696,8 @@ int mcq_run(mcq_ctx *ctx, const mcq_run_params *p) {
         auto max_ctas = [&](int lpc) {   // residency limit: registers, warps, shared memory
             const size_t need = cta_smem(lpc);
             if (need > smem_block) return 0;
-            return (int)std::min<size_t>((size_t)(32 / w), smem_sm / (round_up((int)need, 1024) + 1024));
+            // registers: the kernel is compiled for MCQ_SPEC_MINB CTAs of 4 warps per SM
+            return (int)std::min<size_t>((size_t)(MCQ_SPEC_MINB * 4 / w), smem_sm / (round_up((int)need, 1024) + 1024));
         };
         // relative throughput of one SM vs resident warps (measured, N=12 full_3d, single full wave)
         auto rate = [&](int lpc, int warps) {

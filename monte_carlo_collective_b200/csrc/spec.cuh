@@ -37,7 +37,7 @@
 namespace mcq {
 
 #ifndef MCQ_SPEC_MINB
-#define MCQ_SPEC_MINB 8   // min CTAs (of 4 warps) per SM the register allocation must allow
+#define MCQ_SPEC_MINB 7   // min CTAs (of 4 warps) per SM the register allocation must allow
 #endif
 constexpr int MAX_NBR_ROUNDS = 8;   // 13*(N-1) <= 256 for every N the uint8 table admits
 
