@@ -53,9 +53,9 @@ I_ALG = {"full_3d": 48.0, "board": 40.0}
 ISSUE_PER_CLK_PER_SM = 4
 # ncu measurements of the dominant kernel on this workload (profiles/README.md says which capture)
 AS_BUILT = {"source": "profiles/r1_spec_kernel_raw.txt (ncu --set full, chunk launch of 20480 chains x 26208 steps)",
-            "warp_inst_per_proposal": 14.9, "issue_active_pct": 71.4, "warps_active_per_scheduler": 7.1,
-            "registers_per_thread": 64, "smem_wavefronts_per_proposal": 3.5, "smem_wavefront_pct_of_peak": 63.1,
-            "dram_bytes_per_launch": 1.065e9, "algorithmic_bytes_per_launch": 1.073e9}
+            "warp_inst_per_proposal": 11.2, "issue_active_pct": 70.0, "warps_active_per_scheduler": 6.3,
+            "registers_per_thread": 72, "smem_wavefronts_per_proposal": 2.65, "smem_wavefront_pct_of_peak": 63.7,
+            "dram_bytes_per_launch": 1.056e9, "algorithmic_bytes_per_launch": 1.073e9}
 
 
 class ClockSampler:
