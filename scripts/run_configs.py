@@ -61,9 +61,20 @@ out["C5_sample"] = {"chains": 65536, "n_steps": ns, "kernel_ms": r5.kernel_ms, "
                     "mean_best_energy": float(r5.best_energy.mean()), "acceptance": float(r5.n_accepted.mean()) / ns,
                     "note": "N=64 needs 121 KB of line counters per chain: one thread per chain, counters in global memory (8.3 GB); "
                             "bounded sample of the hot start of C5 (65536 chains x 1e7 steps = 6.6e11 proposals)"}
+# ---- C5 in full (MCQ_FULL_C5=1): 65536 chains x 1e7 steps = 6.55e11 proposals, launches of 5e5 steps ----
+if os.environ.get("MCQ_FULL_C5") == "1":
+    ns = 10000000
+    betas = schedules.beta_table(LIN, ns)
+    t0 = time.time()
+    r5 = eng.run("board", 64, ns, np.arange(65536, dtype=np.uint64), betas, history="none", want_states=False, chunk_steps=500000)
+    out["C5_full"] = {"chains": 65536, "n_steps": ns, "kernel_ms": r5.kernel_ms, "wall_s": time.time() - t0,
+                      "proposals_per_s": 65536.0 * ns / (r5.kernel_ms * 1e-3), "gpu_launches": int(r5.gpu_launches),
+                      "mean_best_energy": float(r5.best_energy.mean()), "min_best_energy": int(r5.best_energy.min()),
+                      "mean_final_energy": float(r5.final_energy.mean()), "mean_initial_energy": float(r5.initial_energy.mean()),
+                      "acceptance": float(r5.n_accepted.mean()) / ns}
 path = os.path.join(ROOT, "profiles", "r1_configs.json")
 json.dump(out, open(path, "w"), indent=1)
-print(json.dumps({k: (v if k == "device" else {kk: vv for kk, vv in v.items() if kk in ("wall_s", "proposals_per_s", "best_pair", "best_energies")}) for k, v in out.items()}))
+print(json.dumps({k: (v if k == "device" else {kk: vv for kk, vv in v.items() if kk in ("wall_s", "proposals_per_s", "best_pair", "best_energies", "mean_best_energy", "min_best_energy", "acceptance", "kernel_ms")}) for k, v in out.items()}))
 print("mean min energy (random):", [round(x, 1) for x in out["C3"]["mean_min_energy"]["random"]])
 print("mean min energy (klarner):", [round(x, 1) for x in out["C3"]["mean_min_energy"]["klarner"]])
 print("mean min energy (latin):", [round(x, 1) for x in out["C3"]["mean_min_energy"]["latin"]])
