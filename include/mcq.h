@@ -59,6 +59,7 @@ extern "C" {
 #define MCQ_ALGO_LINES 1  /* per-line occupancy counters, `lanes_per_chain` lanes per chain (anneal.cuh) */
 #define MCQ_ALGO_TABLE 2  /* per-cell conflict table, one warp per chain, speculative rounds (spec.cuh) */
 #define MCQ_ALGO_GMEM 3   /* line counters in global memory, one thread per chain: boards too large for shared memory */
+#define MCQ_ALGO_WIDE 4   /* line counters in shared memory, one CTA per chain, speculative rounds of 256 steps (wide.cuh) */
 
 /* error codes */
 #define MCQ_OK 0

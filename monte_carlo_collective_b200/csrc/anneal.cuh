@@ -104,6 +104,7 @@ struct KArgs {
     int gslab_dummy;       // index of the dummy slab
     unsigned char *gslab;  // line-counter kernel with G == 1: slabs live in global memory ([n_chains + 1][lay.stride],
                            // the last one a zeroed dummy for the padding threads of the last CTA); null = shared memory
+    int w_best, w_ring, w_xch;   // CTA-per-chain kernel (wide.cuh): byte offsets of the best-state copy, the word ring, the exchange words
     const uint16_t *nbr;   // conflict-table kernel: neighbour lists [N^3][sl.nbr_len]
     const uint32_t *geo;   // conflict-table kernel, full_3d: shared-line bits then wide ids (sl.cta_bytes)
 };

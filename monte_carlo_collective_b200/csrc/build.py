@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 OUT = os.path.join(PKG, "libmcq.so")
 SOURCES = ["mcq_api.cu"]
-HEADERS = ["anneal.cuh", "spec.cuh", "philox.cuh", os.path.join("..", "..", "include", "mcq.h")]
+HEADERS = ["anneal.cuh", "spec.cuh", "wide.cuh", "philox.cuh", os.path.join("..", "..", "include", "mcq.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

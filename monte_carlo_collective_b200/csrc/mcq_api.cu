@@ -18,7 +18,7 @@
 
 #include "../../include/mcq.h"
 #include "anneal.cuh"
-#include "spec.cuh"
+#include "wide.cuh"
 
 namespace mcq {
 
@@ -399,6 +399,20 @@ static cudaError_t launch_spec_lpc(const KArgs &a, bool replay, int grid, int bl
     return replay ? launch_spec_one<false, true, false, 0, LPC>(a, grid, block, smem, s) : launch_spec_nr<false, LPC>(a, grid, block, smem, s);
 }
 
+template <bool FULL, bool EARLY>
+static cudaError_t launch_wide_one(const KArgs &a, int grid, size_t smem, cudaStream_t s) {
+    auto k = wide_kernel<FULL, EARLY>;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin);
+    if (e != cudaSuccess) return e;
+    k<<<grid, WIDE_THREADS, smem, s>>>(a);
+    return cudaGetLastError();
+}
+
+static cudaError_t launch_wide(const KArgs &a, int grid, size_t smem, cudaStream_t s) {
+    if (a.full) return launch_wide_one<true, false>(a, grid, smem, s);
+    return a.patience >= 0 ? launch_wide_one<false, true>(a, grid, smem, s) : launch_wide_one<false, false>(a, grid, smem, s);
+}
+
 static cudaError_t launch_spec(int lpc, const KArgs &a, bool replay, int grid, int block, size_t smem, cudaStream_t s) {
     return lpc == 16 ? launch_spec_lpc<16>(a, replay, grid, block, smem, s) : launch_spec_lpc<32>(a, replay, grid, block, smem, s);
 }
@@ -652,24 +666,30 @@ int mcq_run(mcq_ctx *ctx, const mcq_run_params *p) {
     const size_t smem_sm = ctx->prop.sharedMemPerMultiprocessor;
     int G = p->lanes_per_chain;
     if (G != 0 && G != 4 && G != 8 && G != 16 && G != 32) return fail(MCQ_EINVAL, "lanes_per_chain must be 0, 4, 8, 16 or 32");
-    if (p->algo < MCQ_ALGO_AUTO || p->algo > MCQ_ALGO_GMEM) return fail(MCQ_EINVAL, "unknown algo");
+    if (p->algo < MCQ_ALGO_AUTO || p->algo > MCQ_ALGO_WIDE) return fail(MCQ_EINVAL, "unknown algo");
     if (p->algo == MCQ_ALGO_TABLE && !spec_eligible(full, p->n)) return fail(MCQ_EINVAL, "MCQ_ALGO_TABLE serves N <= 20 (full_3d) or N <= 21 (board)");
     const bool use_spec = p->algo == MCQ_ALGO_TABLE || (p->algo == MCQ_ALGO_AUTO && G == 0 && spec_eligible(full, p->n));
     // Boards whose line counters leave room for only a few chains per SM run one thread per chain with the
     // counters in global memory (HBM-bound byte traffic instead of a latency-bound handful of warps).
     const bool use_gmem = !use_spec && (p->algo == MCQ_ALGO_GMEM ||
         (p->algo == MCQ_ALGO_AUTO && G == 0 && (size_t)make_layout(full, p->n, p->q, 32).stride * MCQ_GMEM_MIN_CHAINS_PER_SM > smem_sm));
-    if (use_gmem) G = 1;
+    // One CTA per chain on shared-memory line counters (wide.cuh); production runs only.
+    const bool use_wide = !use_spec && !use_gmem && p->algo == MCQ_ALGO_WIDE;
+    if (use_wide && replay) return fail(MCQ_EINVAL, "MCQ_ALGO_WIDE does not replay recorded streams");
+    if (use_gmem || use_wide) G = 1;
     if (G == 0) {
         G = 8;
         while (G < 32 && (size_t)make_layout(full, p->n, p->q, G).stride * (32 / G) > smem_block) G *= 2;
     }
     Layout lay = make_layout(full, p->n, p->q, G);
-    if (!use_gmem && (size_t)lay.stride * (32 / G) > smem_block) return fail(MCQ_ENOMEM, "a warp's chains do not fit in shared memory; raise lanes_per_chain");
+    const int w_best = lay.off_pkt, w_ring = w_best + round_up(lay.off_occ - lay.off_state, 16), w_xch = w_ring + WIDE_RING * 16;
+    const size_t wide_smem = (size_t)w_xch + WIDE_XCH_BYTES;
+    if (use_wide && wide_smem > smem_block) return fail(MCQ_ENOMEM, "the line counters of one chain do not fit in shared memory");
+    if (!use_gmem && !use_wide && (size_t)lay.stride * (32 / G) > smem_block) return fail(MCQ_ENOMEM, "a warp's chains do not fit in shared memory; raise lanes_per_chain");
     int wpc = p->warps_per_cta;
     if (wpc < 0 || wpc > 8) return fail(MCQ_EINVAL, "warps_per_cta must be in [0, 8]");
     int best_w = 1, best_chains = 0, best_ctas = 1;
-    for (int w = 8; w >= 1 && !use_gmem; --w) {
+    for (int w = 8; w >= 1 && !use_gmem && !use_wide; --w) {
         if (wpc && w != wpc) continue;
         const int cpc_w = w * 32 / G;
         const size_t need = (size_t)cpc_w * lay.stride;
@@ -678,11 +698,11 @@ int mcq_run(mcq_ctx *ctx, const mcq_run_params *p) {
         ctas = std::min(ctas, 64 / w);
         if (ctas * cpc_w > best_chains) { best_chains = ctas * cpc_w; best_w = w; best_ctas = ctas; }
     }
-    if (best_chains == 0 && !use_gmem) return fail(MCQ_ENOMEM, "requested warps_per_cta does not fit in shared memory");
-    int cpc = use_gmem ? 128 : best_w * 32 / G;
-    int block = use_gmem ? 128 : best_w * 32;
+    if (best_chains == 0 && !use_gmem && !use_wide) return fail(MCQ_ENOMEM, "requested warps_per_cta does not fit in shared memory");
+    int cpc = use_gmem ? 128 : use_wide ? 1 : best_w * 32 / G;
+    int block = use_gmem ? 128 : use_wide ? WIDE_THREADS : best_w * 32;
     int grid = (nc + cpc - 1) / cpc;
-    size_t smem = use_gmem ? 0 : (size_t)cpc * lay.stride;
+    size_t smem = use_gmem ? 0 : use_wide ? wide_smem : (size_t)cpc * lay.stride;
     const SLayout sl = make_spec_layout(full, p->n, p->q);
     int spec_lpc = 32;
     if (use_spec) {
@@ -729,7 +749,7 @@ int mcq_run(mcq_ctx *ctx, const mcq_run_params *p) {
         if (getenv("MCQ_DEBUG"))
             fprintf(stderr, "[mcq] table kernel: lanes/chain %d, %d warps/CTA, %d CTAs/SM (max %d), grid %d, smem %zu B, score %.3f\n",
                     spec_lpc, w, best_ctas_spec, max_ctas(spec_lpc), grid, smem, best_score);
-    } else if (!use_gmem) {   // cap residency (explicit limit, or balance the waves) by padding the shared-memory request
+    } else if (!use_gmem && !use_wide) {   // cap residency (explicit limit, or balance the waves) by padding the shared-memory request
         int ctas = best_ctas;
         const int sms = ctx->prop.multiProcessorCount;
         if (p->max_chains_per_sm > 0) ctas = std::max(1, std::min(ctas, p->max_chains_per_sm / cpc));
@@ -753,6 +773,7 @@ int mcq_run(mcq_ctx *ctx, const mcq_run_params *p) {
     a.patience = (!full && p->early_stop_patience >= 0) ? p->early_stop_patience : -1;
     a.lay = lay;
     a.sl = sl;
+    a.w_best = w_best; a.w_ring = w_ring; a.w_xch = w_xch;
     if (use_spec) {
         DevBuf &nb = ctx->nbr[full * 256 + p->n];
         if (!nb.p) {
@@ -946,7 +967,8 @@ int mcq_run(mcq_ctx *ctx, const mcq_run_params *p) {
             cudaStream_t sb = sub_stream[b];
             a.chain_begin = lo; a.n_chains = hi;
             CUDA_TRY(use_spec ? launch_spec(spec_lpc, a, replay, cta_hi - cta_lo, block, smem, sb)
-                              : launch_anneal(G, a, replay, cta_hi - cta_lo, block, smem, sb));
+                     : use_wide ? launch_wide(a, cta_hi - cta_lo, smem, sb)
+                                : launch_anneal(G, a, replay, cta_hi - cta_lo, block, smem, sb));
             ++launches;
             if (want_stats && n_cols > 0) {
                 const char *hb = direct ? static_cast<const char *>(p->energy_history) + (size_t)h0 * esz : static_cast<const char *>(a.hist);

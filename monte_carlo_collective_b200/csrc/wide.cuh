@@ -1,0 +1,344 @@
+// Speculative CTA-per-chain annealing kernel on line counters (sm_100a): the large-board path.
+//
+// Boards beyond the conflict-table kernel (N > 20 full_3d, N > 21 board; C5 is N = 64 with 4096 queens)
+// keep one uint8 counter per attack line (anneal.cuh) -- 121 KB at N = 64, i.e. ONE chain per SM.  A single
+// warp stepping through such a chain is latency-bound, and one thread per chain with the counters in
+// global memory (anneal_kernel<1> + gslab) is bound by 25 random HBM sectors per proposal.  Here the whole
+// CTA works on one chain, the same way the lanes of a warp do in spec.cuh:
+//
+//   * thread l evaluates the proposal of step t+l against the current state (Philox words of step s depend on
+//     (seed, s) only and are kept in a ring of 2*blockDim steps); delta-E is 2 x 13 (12) counter loads;
+//   * the first accepted thread of the CTA is found with one ballot per warp and a minimum over the warps'
+//     candidates in shared memory; all steps before it were rejected and do not change the state, so the
+//     sequential chain of experiments.py:218-258 / :308-355 is reproduced exactly;
+//   * the winner's warp applies the move: lane f updates the two counters of family f, lane 0 the state;
+//   * two __syncthreads per round.  At the acceptance rates of a cold chain (~1 %) a round of 256 threads
+//     retires ~90 proposals;
+//   * the number of threads that evaluate (`width`, 32..256 in whole warps) follows the acceptance rate: a hot
+//     chain commits after a handful of steps, so evaluating 256 of them would only queue up shared-memory
+//     traffic.  The trajectory does not depend on the width -- any number of speculative steps commits the
+//     same first acceptance.
+//
+// Random stream, proposal rule and Metropolis test are those of anneal_kernel, bit for bit: the same seeds give
+// the same trajectory on either kernel (tests/test_gpu_production.py).
+#pragma once
+#include "spec.cuh"
+
+namespace mcq {
+
+constexpr int WIDE_THREADS = 256;
+constexpr int WIDE_RING = 2 * WIDE_THREADS;   // steps of random words kept per chain
+constexpr int WIDE_JCAP = 62;                 // journal of state elements changed since the last best-state snapshot
+constexpr int WIDE_XCH_BYTES = 256;           // exchange words (3 per warp), journal count, journal
+
+template <bool FULL, bool EARLY>
+__global__ void __launch_bounds__(WIDE_THREADS, 1) wide_kernel(const __grid_constant__ KArgs a) {
+    constexpr unsigned FULLMASK = 0xffffffffu;
+    constexpr int NT = WIDE_THREADS, NW = NT / 32;
+    constexpr int F0 = FULL ? 0 : 1;              // board mode has no (i,j) column family
+    constexpr int NONE = 0x7fffffff;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int chain = a.chain_begin + blockIdx.x;
+    if (chain >= a.n_chains) return;
+    const int N = a.N;
+    const int pos32 = a.lay.pos32;
+
+    uint8_t *cnt = smem;
+    unsigned char *st = smem + a.lay.off_state;
+    uint32_t *occ = reinterpret_cast<uint32_t *>(smem + a.lay.off_occ);
+    unsigned char *bst = smem + a.w_best;                             // state at the best energy (internal format)
+    uint4 *ring = reinterpret_cast<uint4 *>(smem + a.w_ring);
+    int *xch = reinterpret_cast<int *>(smem + a.w_xch);               // [NW] first accepting thread per warp, [NW] its delta-E, scratch
+    const int st_bytes = a.lay.off_occ - a.lay.off_state;             // internal state bytes, rounded up to 4
+    int *jcount = xch + 3 * NW;                                       // entries in the journal; > WIDE_JCAP: overflowed
+    uint16_t *jrn = reinterpret_cast<uint16_t *>(xch + 3 * NW + 1);
+
+    // ---- build the slab from the external state ----
+    {
+        uint32_t *W = reinterpret_cast<uint32_t *>(smem);
+        for (int w = tid; w < a.lay.off_pkt / 4; w += NT) W[w] = 0u;
+        __syncthreads();
+        const uint8_t *ext = a.state + (size_t)chain * a.state_bytes;
+        for (int qi = tid; qi < a.Q; qi += NT) {
+            int i, j, k;
+            if (FULL) {
+                i = ext[3 * qi]; j = ext[3 * qi + 1]; k = ext[3 * qi + 2];
+                store_pos(st, pos32, qi, pack_pos(pos32, i, j, k));
+                const int cid = (i * N + j) * N + k;
+                atomicOr(&occ[cid >> 5], 1u << (cid & 31));
+            } else {
+                i = qi / N; j = qi - i * N; k = ext[qi];
+                st[qi] = (unsigned char)k;
+            }
+#pragma unroll
+            for (int f = F0; f < NFAM; ++f) {
+                const int idx = line_index(a.coef[f], i, j, k);
+                atomicAdd(&W[idx >> 2], 1u << ((idx & 3) * 8));
+            }
+        }
+        __syncthreads();
+    }
+    int E;
+    if (a.t_begin == 0) {
+        const uint32_t *W = reinterpret_cast<const uint32_t *>(smem);
+        int e = 0;
+        for (int w = tid; w < a.lay.n_cnt / 4; w += NT) {
+            const uint32_t v = W[w];
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const int c = (v >> (8 * b)) & 255;
+                e += (c * (c - 1)) >> 1;
+            }
+        }
+        e = __reduce_add_sync(FULLMASK, e);
+        if (lane == 0) xch[2 * NW + warp] = e;
+        __syncthreads();
+        E = 0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) E += xch[2 * NW + w];
+    } else {
+        E = a.cur_e[chain];
+    }
+
+    // ---- persistent record (every thread holds the chain's scalars) ----
+    int best = E, stale = 0, n_acc = 0, best_step = 0, bin_mark = 0;
+    int done = a.t_end;
+    int t = a.t_begin;
+    bool snap = false;   // a new best was reached in this launch: bst holds its state
+    // A new best copies only the state elements moved since the previous snapshot (hot chains set a new best
+    // at almost every acceptance).  jfresh: the journal restarts at the next commit; the first snapshot of a
+    // launch copies everything.
+    bool jfresh = false;
+    if (tid == 0) *jcount = WIDE_JCAP + 1;
+    if (a.t_begin == 0) {
+        if (tid == 0) {
+            if (a.init_e) a.init_e[chain] = E;
+            if (a.hist_kind == 1) reinterpret_cast<uint16_t *>(a.hist)[(size_t)chain * a.hist_pitch] = (uint16_t)E;
+            else if (a.hist_kind == 2) reinterpret_cast<int *>(a.hist)[(size_t)chain * a.hist_pitch] = E;
+        }
+    } else {
+        best = a.best_e[chain];
+        stale = a.stale[chain];
+        n_acc = a.n_acc[chain];
+        best_step = a.best_step[chain];
+        bin_mark = a.bin_mark[chain];
+        const int sd = a.steps_done[chain];
+        if (sd < a.t_begin) { done = sd; t = a.t_end; }   // stopped in an earlier launch
+    }
+    const unsigned long long sd64 = a.seeds ? a.seeds[chain] : 0ull;
+    const uint32_t key0 = (uint32_t)sd64, key1 = (uint32_t)(sd64 >> 32);
+    const float *beta_row = a.beta_c + (size_t)(a.group ? a.group[chain] : 0) * a.n_steps;
+    int bin = a.bin_at_begin;
+    int next_edge = a.n_bins > 0 ? a.bin_starts[bin + 1] : NONE;
+    int tfill = t;
+    int width = 64;   // threads that evaluate a step this round (whole warps)
+    unsigned char *hrow = static_cast<unsigned char *>(a.hist) +
+                          ((long long)chain * a.hist_pitch - a.h_origin) * (a.hist_kind == 1 ? 2 : 4);
+    uint32_t *abits_row = a.abits ? a.abits + (size_t)chain * a.abits_pitch : nullptr;
+
+    while (t < a.t_end) {
+        // ---------------- random words: refill the ring when this round would read past it ----------------
+        if (tfill < t + NT) {
+            const Philox4 w = philox4x32_10((uint32_t)(tfill + tid), 0u, 0u, PHILOX_DOMAIN_STEP, key0, key1);
+            ring[(tfill + tid) & (WIDE_RING - 1)] = make_uint4(w.x, w.y, w.z, w.w);
+            tfill += NT;
+            __syncthreads();
+        }
+        const int rem = min(a.t_end - t, width);
+        const bool valid = tid < rem;
+        const int s = min(t + tid, a.t_end - 1);          // threads past the end redo the last step, masked below
+        const uint4 w = ring[s & (WIDE_RING - 1)];
+        const float cb = __ldg(beta_row + s);
+
+        // ---------------- this thread's proposal: step s against the current state ----------------
+        int i0 = 0, j0 = 0, k0c = 0, i1 = 0, j1 = 0, k1c = 0, qsel = 0, dE = 0;
+        bool accept = false;
+        if (tid < width) {
+        if constexpr (FULL) {
+            qsel = (int)__umulhi(w.x, (uint32_t)a.Q);
+            uint32_t word = w.y;
+            int tries = 0;
+            while (true) {
+                i1 = draw_digit(word, N); j1 = draw_digit(word, N); k1c = draw_digit(word, N);
+                const int cid1 = (i1 * N + j1) * N + k1c;
+                if (!((occ[cid1 >> 5] >> (cid1 & 31)) & 1u)) break;
+                // occupied (the queen's own cell counts, experiments.py:230): redraw
+                if (tries == 0) word = w.w;
+                else if (tries == 1) word = w.x * (uint32_t)a.Q;   // what the queen draw left of word x
+                else {
+                    const int e = tries - 2;
+                    const Philox4 r = philox4x32_10((uint32_t)s, 0u, 1u + (uint32_t)(e >> 2), PHILOX_DOMAIN_STEP, key0, key1);
+                    const int sel = e & 3;
+                    word = sel == 0 ? r.x : sel == 1 ? r.y : sel == 2 ? r.z : r.w;
+                }
+                ++tries;
+            }
+            unpack_pos(pos32, load_pos(st, pos32, qsel), i0, j0, k0c);
+        } else {
+            uint32_t word = w.x;
+            i0 = draw_digit(word, N); j0 = draw_digit(word, N);
+            k0c = st[i0 * N + j0];
+            // uniform over the N-1 other heights (== the redraw loop of experiments.py:317-319)
+            k1c = k0c + 1 + (int)__umulhi(w.y, (uint32_t)(N - 1));
+            k1c -= (k1c >= N) ? N : 0;
+            i1 = i0; j1 = j0;
+        }
+        // delta-E from the line counters: old_conf = sum(co - 1), new_conf = sum(cn) - [shared line]
+        {
+            int io[NFAM], in[NFAM];
+#pragma unroll
+            for (int f = F0; f < NFAM; ++f) {
+                io[f] = line_index(a.coef[f], i0, j0, k0c);
+                in[f] = line_index(a.coef[f], i1, j1, k1c);
+            }
+#pragma unroll
+            for (int f = F0; f < NFAM; ++f) {
+                const int co = cnt[io[f]], cn = cnt[in[f]];
+                // a board move changes k only and every family but the dropped (i,j) one depends on k:
+                // the old and the new cell never share a line
+                if constexpr (FULL) dE += (io[f] != in[f]) ? (cn - co + 1) : 0;
+                else dE += cn - co + 1;
+            }
+        }
+        // Metropolis (experiments.py:238-239 / :326-327): u < exp(-beta dE), u = word / 2^32
+        const float p = exp2f(cb * (float)dE);
+        const uint32_t thr = __float2uint_rz(p * 4294967296.0f);   // saturates at 2^32 - 1
+        accept = valid && ((dE <= 0) || (w.z < thr));
+        }
+
+        // ---------------- the CTA commits its first accepted proposal ----------------
+        // thread index in the high half, delta-E (biased) in the low half: the minimum over the CTA is the first
+        // accepting thread together with its delta-E
+        const int mine = accept ? (tid << 16) | (dE + 0x8000) : NONE;
+        const int wmin = __reduce_min_sync(FULLMASK, mine);
+        if (lane == 0) xch[warp] = wmin;
+        __syncthreads();
+        const int cmin = __reduce_min_sync(FULLMASK, lane < NW ? xch[lane] : NONE);
+        int first = cmin == NONE ? -1 : cmin >> 16;
+        int adv = first >= 0 ? first + 1 : rem;            // steps consumed by this round
+        int adv_h = adv;                                   // steps whose energy is appended to the history
+        bool stop = false;
+        int E_new = first >= 0 ? E + (cmin & 0xffff) - 0x8000 : E;
+        bool improved = E_new < best;
+        if constexpr (EARLY) {
+            // experiments.py:343-353: the counter resets on a strict improvement only, and the
+            // break happens before the history append of the stopping step
+            const int e_stop = max(a.patience - stale - 1, 0);   // rejected step at which patience runs out
+            if (first < 0 || first > e_stop) {
+                if (e_stop < rem) { stop = true; first = -1; adv = e_stop + 1; adv_h = e_stop; stale += e_stop + 1; E_new = E; improved = false; }
+                else stale += adv;
+            } else {
+                stale = improved ? 0 : stale + first + 1;
+                if (stale >= a.patience) { stop = true; adv_h = first; }
+            }
+        }
+        const bool has = first >= 0;
+        // history: steps t .. t+adv_h-1; all but an accepted last one keep the old energy
+        if (tid < adv_h && a.hist_kind) {
+            const int v = (tid == first) ? E_new : E;
+            if (a.hist_kind == 1) reinterpret_cast<uint16_t *>(hrow)[s + 1] = (uint16_t)v;
+            else reinterpret_cast<int *>(hrow)[s + 1] = v;
+        }
+        // ---------------- the winner's warp applies the move: lane f owns family f ----------------
+        if (has && warp == (first >> 5)) {
+            const int src = first & 31;
+            const uint32_t po = __shfl_sync(FULLMASK, (uint32_t)(i0 | (j0 << 8) | (k0c << 16)), src);
+            const uint32_t pn = __shfl_sync(FULLMASK, (uint32_t)(i1 | (j1 << 8) | (k1c << 16)), src);
+            const int wq = __shfl_sync(FULLMASK, qsel, src);
+            const int a0 = po & 255, b0 = (po >> 8) & 255, c0 = po >> 16, a1 = pn & 255, b1 = (pn >> 8) & 255, c1 = pn >> 16;
+            if (lane >= F0 && lane < NFAM) {
+                const int4 cf = a.coef[lane];
+                const int o = line_index(cf, a0, b0, c0), n = line_index(cf, a1, b1, c1);
+                if (o != n) { cnt[o] = (uint8_t)(cnt[o] - 1); cnt[n] = (uint8_t)(cnt[n] + 1); }
+            }
+            if (lane == 31) {
+                const int jn = jfresh ? 0 : *jcount;
+                if (jn < WIDE_JCAP) jrn[jn] = (uint16_t)(FULL ? wq : a0 * N + b0);
+                *jcount = jn + 1;   // WIDE_JCAP + 1 and beyond: overflow, the next snapshot is a full copy
+                if constexpr (FULL) {
+                    const int cid0 = (a0 * N + b0) * N + c0, cid1 = (a1 * N + b1) * N + c1;
+                    occ[cid0 >> 5] &= ~(1u << (cid0 & 31));
+                    occ[cid1 >> 5] |= 1u << (cid1 & 31);
+                    store_pos(st, pos32, wq, pack_pos(pos32, a1, b1, c1));
+                } else {
+                    st[a0 * N + b0] = (unsigned char)c1;
+                }
+            }
+        }
+        __syncthreads();   // counters and state are final before the next round (and before a snapshot) reads them
+
+        // ---------------- bookkeeping ----------------
+        const int n_before = n_acc;
+        if (has) { E = E_new; ++n_acc; jfresh = false; }
+        if (t + adv - 1 >= next_edge || improved || stop || (has && abits_row != nullptr)) {
+            // acceptance bins: close every bin that ends at or before the last consumed step
+            while (t + adv - 1 >= next_edge) {
+                if (tid == 0 && a.acc_hist) a.acc_hist[(size_t)chain * a.n_bins + bin] = (uint32_t)(n_before - bin_mark);
+                bin_mark = n_before;
+                ++bin;
+                next_edge = a.bin_starts[bin + 1];
+            }
+            if (has) {
+                const int ta = t + first;
+                if (tid == 0 && abits_row) atomicOr(abits_row + (ta >> 5), 1u << (ta & 31));
+                if (improved) {
+                    // snapshot: the state at the first visit of the minimum (strict <, :252 / :340); kept in
+                    // shared memory and written out once, when the launch ends
+                    best = E;
+                    if (!stop) best_step = ta + 1;
+                    snap = true;
+                    const int jn = *jcount;
+                    if (jn <= WIDE_JCAP) {
+                        if (tid < jn) {
+                            const int el = jrn[tid];
+                            if constexpr (FULL) store_pos(bst, pos32, el, load_pos(st, pos32, el));
+                            else bst[el] = st[el];
+                        }
+                    } else {
+                        for (int b = tid * 4; b < st_bytes; b += NT * 4)
+                            *reinterpret_cast<uint32_t *>(bst + b) = *reinterpret_cast<const uint32_t *>(st + b);
+                    }
+                    jfresh = true;
+                }
+            }
+            if (stop) {
+                done = t + adv - 1;
+                if (tid == 0 && a.acc_hist) a.acc_hist[(size_t)chain * a.n_bins + bin] = (uint32_t)(n_acc - bin_mark);
+            }
+        }
+        t = stop ? a.t_end : t + adv;
+        // widen when the round was (nearly) used up, narrow when most of it was discarded
+        if (adv * 2 > width) width = min(NT, width * 2);
+        else if (adv * 8 < width) width = max(32, width >> 1);
+    }
+
+    // ---------------- write the record back ----------------
+    __syncthreads();
+    if (tid == 0) {
+        if (a.t_end == a.n_steps && a.n_bins > 0 && a.acc_hist && done == a.t_end)
+            a.acc_hist[(size_t)chain * a.n_bins + bin] = (uint32_t)(n_acc - bin_mark);
+        a.cur_e[chain] = E;
+        a.best_e[chain] = best;
+        a.best_step[chain] = best_step;
+        a.n_acc[chain] = n_acc;
+        a.stale[chain] = stale;
+        a.bin_mark[chain] = bin_mark;
+        a.steps_done[chain] = done;
+    }
+    for (int pass = 0; pass < 2; ++pass) {
+        if (pass == 1 && !snap) break;
+        const unsigned char *src = pass == 0 ? st : bst;
+        uint8_t *out = (pass == 0 ? a.state : a.best_state) + (size_t)chain * a.state_bytes;
+        if constexpr (FULL) {
+            for (int qi = tid; qi < a.Q; qi += NT) {
+                int i, j, k;
+                unpack_pos(pos32, load_pos(src, pos32, qi), i, j, k);
+                out[3 * qi] = (uint8_t)i; out[3 * qi + 1] = (uint8_t)j; out[3 * qi + 2] = (uint8_t)k;
+            }
+        } else {
+            for (int c = tid; c < a.Q; c += NT) out[c] = src[c];
+        }
+    }
+}
+
+}  // namespace mcq

@@ -299,7 +299,7 @@ class Engine:
         p.gpu_launches = C.addressof(launches)
         p.lanes_per_chain, p.warps_per_cta = lanes_per_chain, warps_per_cta
         p.chunk_steps, p.max_chains_per_sm = chunk_steps, max_chains_per_sm
-        p.algo = {"auto": 0, "lines": 1, "table": 2, "gmem": 3}.get(algo, algo)
+        p.algo = {"auto": 0, "lines": 1, "table": 2, "gmem": 3, "wide": 4}.get(algo, algo)
         p.stream = stream
         _lib.check(self._lib.mcq_run(self._h, C.byref(p)))
         res.kernel_ms, res.gpu_launches = float(ms.value), int(launches.value)

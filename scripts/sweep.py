@@ -110,3 +110,20 @@ if which == "gm":
 
 if which == "gmprof":
     run("gmprof", "board", 64, 16384, 3000, algo="gmem")
+
+if which == "wide":
+    for mode, n, nc, ns in (("board", 64, 1184, 20000), ("board", 64, 1184, 200000), ("board", 33, 1184, 100000), ("full_3d", 40, 1184, 50000)):
+        run("wide", mode, n, nc, ns, algo="wide")
+    run("wide-gmem", "board", 64, 16384, 20000, algo="gmem")
+
+if which == "widex":
+    for nc in (148, 1184, 4736, 16384):
+        for algo in ("wide", "gmem"):
+            run("widex", "board", 64, nc, 100000, algo=algo)
+    run("widex", "board", 64, 148, 100000, algo="lines")
+    for nc in (148, 1184, 8192):
+        for algo in ("wide", "gmem", "lines"):
+            run("widex", "board", 30, nc, 100000, algo=algo)
+
+if which == "wideprof":
+    run("wideprof", "board", 64, 148, 50000, algo="wide")

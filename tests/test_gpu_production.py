@@ -60,7 +60,8 @@ def test_same_seed_same_chain_any_layout(engine, mode):
                dict(algo="table", warps_per_cta=1), dict(algo="table", chunk_steps=96, warps_per_cta=2),
                dict(algo="table", lanes_per_chain=32), dict(algo="table", lanes_per_chain=16, warps_per_cta=3),
                dict(algo="table", lanes_per_chain=32, chunk_steps=64), dict(algo="table", lanes_per_chain=16, chunk_steps=64),
-               dict(algo="lines", chunk_steps=320, warps_per_cta=3), dict(algo="gmem"), dict(algo="gmem", chunk_steps=160)):
+               dict(algo="lines", chunk_steps=320, warps_per_cta=3), dict(algo="gmem"), dict(algo="gmem", chunk_steps=160),
+               dict(algo="wide"), dict(algo="wide", chunk_steps=160), dict(algo="wide", chunk_steps=32)):
         r = engine.run(mode, n, ns, seeds, betas, history="full", accept_bits=True, **kw)
         assert (r.energy_history == base.energy_history).all(), kw
         assert (r.best_state == base.best_state).all(), kw
@@ -103,6 +104,26 @@ def test_group_statistics(engine, mode):
     assert full.n_accepted[groups == 1].mean() < full.n_accepted[groups == 0].mean()
 
 
+@pytest.mark.parametrize("mode,n", [("board", 33), ("board", 64), ("full_3d", 24), ("full_3d", 40), ("board", 5), ("full_3d", 3)])
+def test_cta_per_chain_kernel_on_large_boards(engine, mode, n):
+    """The CTA-per-chain speculative kernel (MCQ_ALGO_WIDE) walks the same trajectory as the line-counter kernels."""
+    ns, nc = 1800, 10
+    betas = np.stack([schedules.beta_table(LIN, ns), schedules.beta_table({"type": "constant", "beta_const": 0.3}, ns)])
+    groups = (np.arange(nc) % 2).astype(np.int32)          # a cold and a hot schedule (many / few steps per round)
+    seeds = np.arange(nc, dtype=np.uint64) * 11 + 5
+    base = engine.run(mode, n, ns, seeds, betas, groups=groups, history="full", accept_bits=True, n_bins=50, algo="gmem")
+    _check_invariants(engine, mode, n, base)
+    for kw in (dict(), dict(chunk_steps=256), dict(chunk_steps=1000)):
+        r = engine.run(mode, n, ns, seeds, betas, groups=groups, history="full", accept_bits=True, n_bins=50, algo="wide", **kw)
+        for name in ("energy_history", "initial_energy", "final_energy", "best_energy", "steps_to_best", "n_accepted", "steps_done",
+                     "final_state", "best_state", "accept_bits", "accept_hist"):
+            assert (getattr(r, name) == getattr(base, name)).all(), (kw, name)
+    st = engine.run(mode, n, ns, seeds, betas, groups=groups, history="stats", algo="wide", chunk_steps=512)
+    h = base.energy_history.astype(np.int64)
+    for g in range(2):
+        assert (h[groups == g].sum(axis=0) == st.stat_sum_e[g]).all()
+
+
 def test_initial_states(engine):
     from oracle import queens_numpy as qn
     for n in (5, 11, 12, 14):
@@ -141,7 +162,7 @@ def test_early_stop_board(engine):
     stop = engine.run("board", n, ns, seeds, betas, history="full", accept_bits=True, early_stop_patience=300, n_bins=100)
     assert (stop.steps_done < ns).any()
     for kw in (dict(algo="lines"), dict(algo="lines", lanes_per_chain=32, chunk_steps=128), dict(algo="table", chunk_steps=64),
-               dict(algo="gmem"), dict(algo="gmem", chunk_steps=96),
+               dict(algo="gmem"), dict(algo="gmem", chunk_steps=96), dict(algo="wide"), dict(algo="wide", chunk_steps=96),
                dict(algo="table", lanes_per_chain=32), dict(algo="table", lanes_per_chain=16, chunk_steps=160)):
         other = engine.run("board", n, ns, seeds, betas, history="full", accept_bits=True, early_stop_patience=300,
                            n_bins=100, **kw)
@@ -158,9 +179,10 @@ def test_early_stop_board(engine):
                            algo="table", lanes_per_chain=lanes)
             for name in ("steps_done", "final_energy", "best_energy", "steps_to_best", "n_accepted", "final_state", "best_state", "accept_bits"):
                 assert (getattr(c, name) == getattr(a, name)[:33]).all(), (pat, lanes, name)
-        b = engine.run("board", n, 400, seeds, betas[:400], history="full", accept_bits=True, early_stop_patience=pat, algo="lines")
-        for name in ("steps_done", "final_energy", "best_energy", "steps_to_best", "n_accepted", "final_state", "best_state", "accept_bits"):
-            assert (getattr(a, name) == getattr(b, name)).all(), (pat, name)
+        for algo in ("lines", "wide"):
+            b = engine.run("board", n, 400, seeds, betas[:400], history="full", accept_bits=True, early_stop_patience=pat, algo=algo)
+            for name in ("steps_done", "final_energy", "best_energy", "steps_to_best", "n_accepted", "final_state", "best_state", "accept_bits"):
+                assert (getattr(a, name) == getattr(b, name)).all(), (pat, algo, name)
     for c in range(len(seeds)):
         d = int(stop.steps_done[c])
         assert (stop.energy_history[c, : d + 1] == free.energy_history[c, : d + 1]).all()
