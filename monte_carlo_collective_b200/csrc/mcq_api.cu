@@ -671,11 +671,23 @@ int mcq_run(mcq_ctx *ctx, const mcq_run_params *p) {
     const bool use_spec = p->algo == MCQ_ALGO_TABLE || (p->algo == MCQ_ALGO_AUTO && G == 0 && spec_eligible(full, p->n));
     // Boards whose line counters leave room for only a few chains per SM run one thread per chain with the
     // counters in global memory (HBM-bound byte traffic instead of a latency-bound handful of warps).
-    const bool use_gmem = !use_spec && (p->algo == MCQ_ALGO_GMEM ||
+    bool use_gmem = !use_spec && (p->algo == MCQ_ALGO_GMEM ||
         (p->algo == MCQ_ALGO_AUTO && G == 0 && (size_t)make_layout(full, p->n, p->q, 32).stride * MCQ_GMEM_MIN_CHAINS_PER_SM > smem_sm));
-    // One CTA per chain on shared-memory line counters (wide.cuh); production runs only.
-    const bool use_wide = !use_spec && !use_gmem && p->algo == MCQ_ALGO_WIDE;
+    // One CTA per chain on shared-memory line counters (wide.cuh); production runs only.  It is the default beyond
+    // the conflict table's reach: 3-20x faster than a warp or a thread per chain when the chains are few, and
+    // ahead on long anneals at any count (a cold chain retires ~60 proposals per round).  Only short, hot runs
+    // of very many chains are left to the global-memory kernel (measured crossover at N = 64: 32 chains per SM
+    // below 1e6 steps).
+    bool use_wide = !use_spec && p->algo == MCQ_ALGO_WIDE;
     if (use_wide && replay) return fail(MCQ_EINVAL, "MCQ_ALGO_WIDE does not replay recorded streams");
+    {
+        const Layout l1 = make_layout(full, p->n, p->q, 1);
+        const size_t need = (size_t)l1.off_pkt + round_up(l1.off_occ - l1.off_state, 16) + WIDE_RING * 16 + WIDE_XCH_BYTES;
+        if (p->algo == MCQ_ALGO_AUTO && !use_spec && !replay && G == 0 && need <= smem_block &&
+            !(use_gmem && nc >= 32 * ctx->prop.multiProcessorCount && ns < 1000000))
+            use_wide = true;
+    }
+    if (use_wide) use_gmem = false;
     if (use_gmem || use_wide) G = 1;
     if (G == 0) {
         G = 8;

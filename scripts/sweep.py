@@ -127,3 +127,9 @@ if which == "widex":
 
 if which == "wideprof":
     run("wideprof", "board", 64, 148, 50000, algo="wide")
+
+if which == "widelong":
+    for ns in (300000, 1000000, 4000000):
+        run("widelong", "board", 64, 148, ns, algo="wide")
+    run("widelong", "board", 64, 16384, 300000, algo="gmem")
+    run("widelong", "board", 64, 16384, 1000000, algo="gmem")
