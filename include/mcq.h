@@ -55,7 +55,8 @@ extern "C" {
 #define MCQ_HIST_I32 2
 
 /* delta-E data structure / kernel */
-#define MCQ_ALGO_AUTO 0   /* conflict table when its uint8 entries suffice, else line counters */
+#define MCQ_ALGO_AUTO 0   /* conflict table when its entries suffice (N <= 20 / 21), else one CTA per chain on line counters;
+                             replays and short runs of very many large-board chains use LINES / GMEM */
 #define MCQ_ALGO_LINES 1  /* per-line occupancy counters, `lanes_per_chain` lanes per chain (anneal.cuh) */
 #define MCQ_ALGO_TABLE 2  /* per-cell conflict table, one warp per chain, speculative rounds (spec.cuh) */
 #define MCQ_ALGO_GMEM 3   /* line counters in global memory, one thread per chain: boards too large for shared memory */
