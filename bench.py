@@ -58,6 +58,17 @@ AS_BUILT = {"source": "profiles/r1_spec_kernel_raw.txt (ncu --set full, chunk la
             "dram_bytes_per_launch": 1.056e9, "algorithmic_bytes_per_launch": 1.073e9}
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """Print the result line on the process's original stdout."""
+    sys.stdout.flush()
+    if _REAL_STDOUT is not None:
+        os.dup2(_REAL_STDOUT, 1)
+    print(json.dumps(line), flush=True)
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled during the timed region."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -154,7 +165,7 @@ def run_reference_arm(args, rank, world):
         "e2e": {"value": total, "unit": "proposals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args, world, cpu=False):
@@ -189,6 +200,12 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly one JSON line: anything libraries print on the way (NCCL's version banner, build
+    # logs) is sent to stderr, and the real stdout is put back for the final print
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference_arm(args, rank, world)
         return
@@ -350,7 +367,7 @@ def main():
             "metric_full": "MCMC proposals/sec (N=12, 1/2/4/8 B200) vs host-CPU ref; min energy reached",
             "dtype_note": "uint8 conflict table, int32 energies, float32 ex2 accept threshold on a 32-bit uniform word",
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

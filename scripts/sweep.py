@@ -133,3 +133,6 @@ if which == "widelong":
         run("widelong", "board", 64, 148, ns, algo="wide")
     run("widelong", "board", 64, 16384, 300000, algo="gmem")
     run("widelong", "board", 64, 16384, 1000000, algo="gmem")
+
+if which == "wideprof2":
+    run("wideprof2", "board", 64, 148, 1000000, algo="wide")
