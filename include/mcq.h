@@ -33,7 +33,8 @@
 extern "C" {
 #endif
 
-#define MCQ_ABI_VERSION 1
+#define MCQ_ABI_VERSION 2
+#define MCQ_RECORD_INTS 8
 
 /* state space (experiments.py:497-502: "board" or anything else => full_3d) */
 #define MCQ_MODE_BOARD 0  /* one queen per (i,j) column; state = uint8 heights[N*N], row-major (i,j) */
@@ -136,6 +137,21 @@ typedef struct mcq_run_params {
     int32_t max_chains_per_sm;
     int32_t algo;            /* MCQ_ALGO_*; a non-zero lanes_per_chain with AUTO selects LINES */
     void *stream;            /* cudaStream_t, or NULL for the context's own stream */
+
+    /* ---- checkpoint / resume (the reference has none: SURVEY 5.4; chains are resumable here because the random
+     *      stream is counter-based -- step s of a chain depends on (seed, s) only) ----
+     * A call executes steps [start_step, stop_step) of the n_steps-long schedule.  Both are multiples of 32 (or
+     * n_steps); 0 / 0 = the whole run.  A segment with start_step > 0 takes the chains' states at start_step
+     * as `init_states` (MCQ_INIT_EXPLICIT), their records and best states from the previous segment, and
+     * continues into the SAME output arrays: history columns, accept bits, closed acceptance bins and
+     * statistics of earlier segments are preserved (host arrays are uploaded first). */
+    int32_t start_step;
+    int32_t stop_step;
+    const int32_t *resume_record;     /* [MCQ_RECORD_INTS][n_chains]: record_out of the previous segment */
+    const uint8_t *resume_best_state; /* [n_chains][state bytes] */
+    int32_t *record_out;              /* [MCQ_RECORD_INTS][n_chains] (optional): initial, current and best energy, step of the
+                                         best, accepted moves, steps done, steps since the last improvement, accepted
+                                         moves at the start of the open acceptance bin */
 } mcq_run_params;
 
 /* lifetime ------------------------------------------------------------------------- */

@@ -9,12 +9,12 @@ call does, and fails loudly if ``libmcq.so`` has not been built (no CPU fallback
 from .api import (build_schedule_from_params, install, metropolis_mcmc, metropolis_mcmc_board,  # noqa: F401
                   run_experiment, run_single_chain, run_single_chain_board,
                   run_single_chain_board_multithread, run_single_chain_multithread)
-from .engine import BOARD, FULL, Engine, RunResult, default_engine  # noqa: F401
+from .engine import BOARD, FULL, Engine, RunResult, default_engine, load_checkpoint  # noqa: F401
 from .states import State3DQueens, State3DQueensBoard  # noqa: F401
 
 __all__ = [
     "BOARD", "FULL", "Engine", "RunResult", "default_engine", "State3DQueens", "State3DQueensBoard",
     "metropolis_mcmc", "metropolis_mcmc_board", "run_single_chain", "run_single_chain_board",
     "run_single_chain_multithread", "run_single_chain_board_multithread", "run_experiment",
-    "build_schedule_from_params", "install",
+    "build_schedule_from_params", "install", "load_checkpoint",
 ]

@@ -17,7 +17,7 @@ INIT_RANDOM, INIT_LATIN, INIT_KLARNER, INIT_EXPLICIT = 0, 1, 2, 3
 MEM_HOST, MEM_DEVICE = 0, 1
 HIST_NONE, HIST_U16, HIST_I32 = 0, 1, 2
 OK, EINVAL, ECUDA, ENOMEM, EREPLAY = 0, -1, -2, -3, -4
-ABI_VERSION = 1
+ABI_VERSION = 2
 ALGO_AUTO, ALGO_LINES, ALGO_TABLE, ALGO_GMEM = 0, 1, 2, 3
 
 
@@ -75,6 +75,11 @@ class RunParams(C.Structure):
         ("max_chains_per_sm", C.c_int32),
         ("algo", C.c_int32),
         ("stream", C.c_void_p),
+        ("start_step", C.c_int32),
+        ("stop_step", C.c_int32),
+        ("resume_record", C.c_void_p),
+        ("resume_best_state", C.c_void_p),
+        ("record_out", C.c_void_p),
     ]
 
 

@@ -70,6 +70,7 @@ struct KArgs {
     int chain_begin;      // first chain of this launch: CTA 0 starts here
     int n_steps;          // total steps of the schedule (row length of the beta tables)
     int t_begin, t_end;   // this launch covers steps [t_begin, t_end)
+    int t_last;           // the call (segment) ends at this step: global-memory slabs write their state back then
     int patience;         // < 0: none
     Layout lay;
     SLayout sl;
@@ -531,7 +532,7 @@ __global__ void __launch_bounds__(256) anneal_kernel(const __grid_constant__ KAr
             a.acc_hist[(size_t)chain * a.n_bins + bin] = (uint32_t)(n_acc - bin_mark);
         }
         uint8_t *out = a.state + (size_t)chain * a.state_bytes;
-        if (!a.gslab || a.t_end == a.n_steps) {   // a global slab keeps the state between launches
+        if (!a.gslab || a.t_end == a.t_last) {   // a global slab keeps the state between the launches of a call
             if constexpr (FULL) {
                 for (int qi = g; qi < a.Q; qi += G) {
                     int i, j, k;
@@ -562,7 +563,9 @@ __global__ void __launch_bounds__(32) gslab_build_kernel(const __grid_constant__
     const int e = build_chain<32>(a, a.gslab + (size_t)chain * a.lay.stride, a.state + (size_t)chain * a.state_bytes, true, threadIdx.x);
     if (threadIdx.x == 0) {
         a.cur_e[chain] = e;
-        reinterpret_cast<uint16_t *>(a.gslab + (size_t)chain * a.lay.stride + a.lay.off_jrn)[JRN] = 0;   // empty journal
+        // fresh run: best state == state, empty journal; resumed segment: the best state is an older one, so the
+        // journal starts overflowed and the next new best copies the whole state
+        reinterpret_cast<uint16_t *>(a.gslab + (size_t)chain * a.lay.stride + a.lay.off_jrn)[JRN] = a.t_begin > 0 ? JRN + 1 : 0;
     }
 }
 

@@ -651,6 +651,14 @@ int mcq_run(mcq_ctx *ctx, const mcq_run_params *p) {
     const long long e_max = 13LL * p->q * (p->n - 1) / 2;
     if (want_hist && p->hist_dtype == MCQ_HIST_U16 && e_max >= 65536) return fail(MCQ_EINVAL, "uint16 history would overflow for this N; use MCQ_HIST_I32");
     if (p->n_bins < 0 || (p->n_bins > 0 && (!p->bin_starts || !p->accept_hist))) return fail(MCQ_EINVAL, "n_bins > 0 needs bin_starts and accept_hist");
+    // checkpoint / resume: this call executes steps [t_start, t_stop) of the schedule
+    const int t_start = p->start_step, t_stop = p->stop_step > 0 ? p->stop_step : p->n_steps;
+    if (t_start < 0 || t_start > t_stop || t_stop > p->n_steps) return fail(MCQ_EINVAL, "need 0 <= start_step <= stop_step <= n_steps");
+    if (t_start % HBLK != 0 || (t_stop % HBLK != 0 && t_stop != p->n_steps))
+        return fail(MCQ_EINVAL, "start_step and stop_step must be multiples of 32 (stop_step may also be n_steps)");
+    const bool resume = t_start > 0;
+    if (resume && (p->init_mode != MCQ_INIT_EXPLICIT || !p->resume_record || !p->resume_best_state))
+        return fail(MCQ_EINVAL, "start_step > 0 needs init_states (the states at start_step), resume_record and resume_best_state");
     if (p->n_chains == 0) { if (p->kernel_ms) *p->kernel_ms = 0.f; if (p->gpu_launches) *p->gpu_launches = 0; return 0; }
 
     CUDA_TRY(cudaSetDevice(ctx->device));
@@ -781,7 +789,7 @@ int mcq_run(mcq_ctx *ctx, const mcq_run_params *p) {
     // ---- inputs ----
     KArgs a;
     memset(&a, 0, sizeof a);
-    a.full = full; a.N = p->n; a.Q = p->q; a.n_chains = nc; a.n_steps = ns;
+    a.full = full; a.N = p->n; a.Q = p->q; a.n_chains = nc; a.n_steps = ns; a.t_last = t_stop;
     a.patience = (!full && p->early_stop_patience >= 0) ? p->early_stop_patience : -1;
     a.lay = lay;
     a.sl = sl;
@@ -854,13 +862,20 @@ int mcq_run(mcq_ctx *ctx, const mcq_run_params *p) {
         CUDA_TRY(cudaGetLastError());
         ++launches;
     }
-    CUDA_TRY(cudaMemcpyAsync(a.best_state, a.state, (size_t)nc * sbytes, cudaMemcpyDeviceToDevice, s));
+    const cudaMemcpyKind in_kind = mem == MCQ_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    if (resume) {   // the record and the best states continue from the previous segment
+        CUDA_TRY(cudaMemcpyAsync(rec, p->resume_record, (size_t)nc * MCQ_RECORD_INTS * 4, in_kind, s));
+        CUDA_TRY(cudaMemcpyAsync(a.best_state, p->resume_best_state, (size_t)nc * sbytes, in_kind, s));
+    } else {
+        CUDA_TRY(cudaMemcpyAsync(a.best_state, a.state, (size_t)nc * sbytes, cudaMemcpyDeviceToDevice, s));
+    }
     if (use_gmem) {   // slabs in global memory: built once, reused by every launch of this call
         if (ctx->buf[B_GSLAB].ensure(((size_t)nc + 1) * lay.stride)) return fail(MCQ_ENOMEM, "device allocation failed (global-memory slabs)");
         a.gslab = static_cast<unsigned char *>(ctx->buf[B_GSLAB].p);
         a.gslab_dummy = nc;
         CUDA_TRY(cudaMemsetAsync(a.gslab + (size_t)nc * lay.stride, 0, lay.stride, s));
         a.chain_begin = 0;
+        a.t_begin = t_start;
         gslab_build_kernel<<<nc, 32, 0, s>>>(a);
         CUDA_TRY(cudaGetLastError());
         ++launches;
@@ -882,7 +897,8 @@ int mcq_run(mcq_ctx *ctx, const mcq_run_params *p) {
             if (ctx->buf[B_ACCH].ensure((size_t)nc * p->n_bins * 4)) return fail(MCQ_ENOMEM, "device allocation failed");
             a.acc_hist = static_cast<uint32_t *>(ctx->buf[B_ACCH].p);
         }
-        CUDA_TRY(cudaMemsetAsync(a.acc_hist, 0, (size_t)nc * p->n_bins * 4, s));
+        if (!resume) CUDA_TRY(cudaMemsetAsync(a.acc_hist, 0, (size_t)nc * p->n_bins * 4, s));
+        else if (mem == MCQ_MEM_HOST) CUDA_TRY(cudaMemcpyAsync(a.acc_hist, p->accept_hist, (size_t)nc * p->n_bins * 4, cudaMemcpyHostToDevice, s));
     }
 
     // ---- accept bitmap ----
@@ -894,7 +910,9 @@ int mcq_run(mcq_ctx *ctx, const mcq_run_params *p) {
             if (ctx->buf[B_ABITS].ensure((size_t)nc * abits_words * 4 + 4)) return fail(MCQ_ENOMEM, "device allocation failed");
             a.abits = static_cast<uint32_t *>(ctx->buf[B_ABITS].p);
         }
-        CUDA_TRY(cudaMemsetAsync(a.abits, 0, (size_t)nc * abits_words * 4, s));   // the table kernel stores non-zero words only
+        // (the table kernel stores non-zero words only; a resumed segment keeps the bits of the earlier ones)
+        if (!resume) CUDA_TRY(cudaMemsetAsync(a.abits, 0, (size_t)nc * abits_words * 4, s));
+        else if (mem == MCQ_MEM_HOST) CUDA_TRY(cudaMemcpyAsync(a.abits, p->accept_bits, (size_t)nc * abits_words * 4, cudaMemcpyHostToDevice, s));
     }
 
     // ---- statistics accumulators ----
@@ -907,8 +925,13 @@ int mcq_run(mcq_ctx *ctx, const mcq_run_params *p) {
             d_sum_e = static_cast<unsigned long long *>(ctx->buf[B_SUME].p);
             d_sum_e2 = static_cast<unsigned long long *>(ctx->buf[B_SUME2].p);
         }
-        CUDA_TRY(cudaMemsetAsync(d_sum_e, 0, stat_elems * 8, s));
-        CUDA_TRY(cudaMemsetAsync(d_sum_e2, 0, stat_elems * 8, s));
+        if (!resume) {
+            CUDA_TRY(cudaMemsetAsync(d_sum_e, 0, stat_elems * 8, s));
+            CUDA_TRY(cudaMemsetAsync(d_sum_e2, 0, stat_elems * 8, s));
+        } else if (mem == MCQ_MEM_HOST) {
+            CUDA_TRY(cudaMemcpyAsync(d_sum_e, p->stat_sum_e, stat_elems * 8, cudaMemcpyHostToDevice, s));
+            CUDA_TRY(cudaMemcpyAsync(d_sum_e2, p->stat_sum_e2, stat_elems * 8, cudaMemcpyHostToDevice, s));
+        }
     }
 
     // ---- history plan ----
@@ -953,8 +976,8 @@ int mcq_run(mcq_ctx *ctx, const mcq_run_params *p) {
         CUDA_TRY(cudaEventCreateWithFlags(&e_sub[b], cudaEventDisableTiming));
         CUDA_TRY(cudaStreamWaitEvent(sub_stream[b], e_start, 0));
     }
-    for (int t0 = 0, first_pass = 1; t0 < ns || first_pass; first_pass = 0) {
-        const int t1 = std::min(ns, t0 + chunk);
+    for (int t0 = t_start, first_pass = 1; t0 < t_stop || first_pass; first_pass = 0) {
+        const int t1 = std::min(t_stop, t0 + chunk);
         a.t_begin = t0; a.t_end = t1;
         a.hist_kind = hkind;
         if (hkind != MCQ_HIST_NONE) {
@@ -1027,6 +1050,7 @@ int mcq_run(mcq_ctx *ctx, const mcq_run_params *p) {
     if (int rc = copy_out(p->n_accepted, a.n_acc, (size_t)nc * 4, mem, s)) return rc;
     if (int rc = copy_out(p->steps_done, a.steps_done, (size_t)nc * 4, mem, s)) return rc;
     if (int rc = copy_out(p->n_near_threshold, a.near_cnt, (size_t)nc * 4, mem, s)) return rc;
+    if (int rc = copy_out(p->record_out, rec, (size_t)nc * MCQ_RECORD_INTS * 4, mem, s)) return rc;
     if (int rc = copy_out(p->final_state, a.state, (size_t)nc * sbytes, mem, s)) return rc;
     if (int rc = copy_out(p->best_state, a.best_state, (size_t)nc * sbytes, mem, s)) return rc;
     if (mem == MCQ_MEM_HOST) {

@@ -84,12 +84,30 @@ class RunResult:
     n_near_threshold: object = None   # replay only
     kernel_ms: float = 0.0
     gpu_launches: int = 0
+    record: object = None             # [8, n_chains] int32: what a later segment needs besides the states
+    step: int = 0                     # steps [0, step) of the schedule have been executed
+
+    def save_checkpoint(self, path):
+        """Everything needed to continue these chains later (``Engine.run(..., resume=load_checkpoint(path))``
+        with the same seeds and schedule): states, best states, the per-chain record and the step reached."""
+        def host(x):
+            return np.asarray(x.cpu() if hasattr(x, "cpu") else x)
+        np.savez_compressed(path, record=host(self.record), final_state=host(self.final_state), best_state=host(self.best_state),
+                            meta=np.array([self.mode, self.n, self.q, self.n_steps, self.n_chains, self.step], dtype=np.int64))
 
     def accepted_mask(self, chain):
         """bool[n_steps]: step s of ``chain`` was accepted (needs accept_bits)."""
         words = np.asarray(self.accept_bits[chain].cpu() if hasattr(self.accept_bits, "cpu") else self.accept_bits[chain])
         bits = np.unpackbits(words.view(np.uint8), bitorder="little")
         return bits[: self.n_steps].astype(bool)
+
+
+def load_checkpoint(path):
+    """RunResult holding the resumable part of a run written by ``RunResult.save_checkpoint``."""
+    z = np.load(path)
+    mode, n, q, ns, nc, step = (int(v) for v in z["meta"])
+    return RunResult(mode=mode, n=n, q=q, n_steps=ns, n_chains=nc, record=z["record"], final_state=z["final_state"],
+                     best_state=z["best_state"], step=step)
 
 
 def _ptr(x):
@@ -184,7 +202,7 @@ class Engine:
             init_states=None, history="full", hist_dtype=None, accept_bits=False, n_bins=0,
             early_stop_patience=None, replay=None, want_states=True, device_buffers=False,
             beta_device_table=None, lanes_per_chain=0, warps_per_cta=0, chunk_steps=0, max_chains_per_sm=0,
-            algo=0, stream=None, out=None) -> RunResult:
+            algo=0, stream=None, out=None, stop_step=None, resume=None) -> RunResult:
         """Run ``len(seeds)`` independent chains.
 
         seeds   uint64 per chain (the Philox key; reference: ``base_seed + r``, experiments.py:508)
@@ -193,6 +211,11 @@ class Engine:
         replay  dict(moves=[n_chains,n_steps,3|4], uniforms=[n_chains,n_steps]) to consume a recorded
                 stream instead of Philox (float64 accept test; betas must be the exact float64 table)
         out     optional dict of preallocated output buffers to reuse (same keys as RunResult)
+        stop_step  execute the schedule only up to this step (a multiple of 32); the result can be continued
+        resume  a RunResult (or ``load_checkpoint``) of the same chains stopped earlier: execution continues at
+                ``resume.step`` from its states and record, into its history / accept arrays if it has them.
+                Seeds, schedule and n_steps must be those of the first segment (the random words of step s
+                depend on (seed, s) only, so the continued chains are the chains an uninterrupted run produces).
         """
         mode = mode_id(mcmc_type)
         q = n * n if q is None else int(q)
@@ -203,7 +226,17 @@ class Engine:
         seeds_in = self._in(seeds, np.uint64, device_buffers)
         nc = int(seeds_in.shape[0])
         ns = int(n_steps)
-        out = out or {}
+        out = dict(out or {})
+        start = 0
+        if resume is not None:
+            if (resume.mode, resume.n, resume.q, resume.n_steps, resume.n_chains) != (mode, n, q, ns, nc):
+                raise ValueError("resume: the checkpoint belongs to a different problem (mode, N, Q, n_steps or n_chains)")
+            if resume.record is None or resume.final_state is None or resume.best_state is None:
+                raise ValueError("resume needs a result with record, final_state and best_state (want_states=True)")
+            start, init_states = int(resume.step), resume.final_state
+            for name in ("energy_history", "accept_bits", "accept_hist", "stat_sum_e", "stat_sum_e2"):
+                if getattr(resume, name, None) is not None:
+                    out.setdefault(name, getattr(resume, name))
         p = _lib.RunParams()
         p.struct_size = C.sizeof(_lib.RunParams)
         p.mode, p.n, p.q, p.n_steps, p.n_chains = mode, n, q, ns, nc
@@ -301,6 +334,14 @@ class Engine:
         p.chunk_steps, p.max_chains_per_sm = chunk_steps, max_chains_per_sm
         p.algo = {"auto": 0, "lines": 1, "table": 2, "gmem": 3, "wide": 4}.get(algo, algo)
         p.stream = stream
+        p.start_step, p.stop_step = start, int(stop_step or 0)
+        if resume is not None:
+            rr = self._in(resume.record, np.int32, device_buffers)
+            rb = self._in(resume.best_state, np.uint8, device_buffers)
+            keep += [rr, rb]
+            p.resume_record, p.resume_best_state = _ptr(rr), _ptr(rb)
+        p.record_out = buf("record", (8, nc), np.int32)
+        res.step = int(stop_step or ns)
         _lib.check(self._lib.mcq_run(self._h, C.byref(p)))
         res.kernel_ms, res.gpu_launches = float(ms.value), int(launches.value)
         del keep

@@ -92,7 +92,7 @@ def test_c_abi_exports_every_declared_symbol():
         getattr(lib, name)
     assert declared == {name for name, _, _ in _lib.SYMBOLS}
     lib = _lib.load()
-    assert lib.mcq_abi_version() == 1
+    assert lib.mcq_abi_version() == 2
     assert lib.mcq_sizeof_run_params() == C.sizeof(_lib.RunParams)
     # every field of the ctypes mirror appears in the header struct, in order
     body = header[header.index("typedef struct mcq_run_params {"): header.index("} mcq_run_params;")]
@@ -149,3 +149,18 @@ def test_missing_library_is_an_import_error(tmp_path, monkeypatch):
     monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "libmcq.so"))
     with pytest.raises(ImportError, match="no CPU fallback"):
         _lib.load()
+
+
+def test_checkpoint_file_roundtrip(tmp_path):
+    """save_checkpoint / load_checkpoint keep what a later segment needs (no GPU involved)."""
+    import monte_carlo_collective_b200 as mcq
+    from monte_carlo_collective_b200.engine import RunResult
+    rng = np.random.RandomState(3)
+    r = RunResult(mode=mcq.BOARD, n=6, q=36, n_steps=4096, n_chains=5, record=rng.randint(0, 99, size=(8, 5)).astype(np.int32),
+                  final_state=rng.randint(0, 6, size=(5, 6, 6)).astype(np.uint8),
+                  best_state=rng.randint(0, 6, size=(5, 6, 6)).astype(np.uint8), step=1024)
+    r.save_checkpoint(tmp_path / "c.npz")
+    c = mcq.load_checkpoint(tmp_path / "c.npz")
+    assert (c.mode, c.n, c.q, c.n_steps, c.n_chains, c.step) == (r.mode, 6, 36, 4096, 5, 1024)
+    assert (c.record == r.record).all() and (c.final_state == r.final_state).all() and (c.best_state == r.best_state).all()
+    assert c.record.dtype == np.int32 and c.final_state.dtype == np.uint8
