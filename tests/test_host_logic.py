@@ -154,9 +154,9 @@ def test_missing_library_is_an_import_error(tmp_path, monkeypatch):
 def test_checkpoint_file_roundtrip(tmp_path):
     """save_checkpoint / load_checkpoint keep what a later segment needs (no GPU involved)."""
     import monte_carlo_collective_b200 as mcq
-    from monte_carlo_collective_b200.engine import RunResult
+    from monte_carlo_collective_b200.engine import RunResult, mode_id
     rng = np.random.RandomState(3)
-    r = RunResult(mode=mcq.BOARD, n=6, q=36, n_steps=4096, n_chains=5, record=rng.randint(0, 99, size=(8, 5)).astype(np.int32),
+    r = RunResult(mode=mode_id("board"), n=6, q=36, n_steps=4096, n_chains=5, record=rng.randint(0, 99, size=(8, 5)).astype(np.int32),
                   final_state=rng.randint(0, 6, size=(5, 6, 6)).astype(np.uint8),
                   best_state=rng.randint(0, 6, size=(5, 6, 6)).astype(np.uint8), step=1024)
     r.save_checkpoint(tmp_path / "c.npz")
