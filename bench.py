@@ -55,6 +55,7 @@ ISSUE_PER_CLK_PER_SM = 4
 AS_BUILT = {"source": "profiles/r1_spec_kernel_raw.txt (ncu --set full, chunk launch of 20480 chains x 26208 steps)",
             "warp_inst_per_proposal": 11.2, "issue_active_pct": 70.0, "warps_active_per_scheduler": 6.3,
             "registers_per_thread": 72, "smem_wavefronts_per_proposal": 2.65, "smem_wavefront_pct_of_peak": 63.7,
+            "speculated_steps_per_round": 32, "proposals_retired_per_round": 19.4, "cycles_per_round_per_warp": 2080,
             "dram_bytes_per_launch": 1.056e9, "algorithmic_bytes_per_launch": 1.073e9}
 
 
@@ -340,6 +341,8 @@ def main():
         "kernel_proposals_per_s": kernel_pps, "sm_clock_mhz_used": f_mhz, "sm_count": eng.sm_count,
         "as_built": AS_BUILT,
         "frac_under_survey_mapping": kernel_pps * I_ALG["full_3d"] / peak,
+        # shared-memory utilisation with the survey's W_alg = 3 + 1/(N-1) + 3 p wavefronts per proposal
+        "smem_util_survey": kernel_pps * (3.0 + 1.0 / 11.0 + 3.0 * p_acc) / (eng.sm_count * f_mhz * 1e6),
         "hbm": {"algorithmic_bytes_per_proposal": 2.0, "achieved_gbs": kernel_pps * 2.0 / 1e9, "peak_gbs": hbm_peak,
                 "peak_source": "MEASURED_PEAKS.json" if os.path.isfile(peaks_file) else "fallback"},
         "note": "frac = pps * I_alg(p) / (4 * n_SM * f_measured); as_built = ncu on the same kernel (profiles/); "

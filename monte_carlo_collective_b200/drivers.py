@@ -170,3 +170,59 @@ def competition(N=15, n_runs=10, n_steps=100000, beta_start=1.0, beta_end=3.0, b
         print(results[0]["best_state"])
     path = reports.write_best_heights(results[0]["best_state"], out_dir, stamp)
     return results, path
+
+
+def parallel_tempering(N, n_steps, betas, n_ladders=64, swap_every=1024, base_seed=0, init_mode="random",
+                       mcmc_type="board", swap_seed=12345, engine=None):
+    """Replica exchange over a ladder of constant inverse temperatures (NOT in the reference --
+    it changes the chain, so it lives here, off the drop-in path, and the annealing kernels are untouched).
+
+    ``len(betas)`` rungs x ``n_ladders`` independent ladders = that many chains, all in one batch.  The run is cut
+    into segments of ``swap_every`` steps (checkpoint / resume of the engine); after each segment neighbouring
+    rungs of a ladder (even pairs and odd pairs alternately) exchange their temperatures with probability
+    ``min(1, exp((beta_a - beta_b) * (E_a - E_b)))``, which leaves the joint Boltzmann distribution of the ladder
+    invariant.  Exchanging temperatures instead of states means a swap is two integers in the chain -> rung table.
+
+    Returns a dict: best_energy / best_state per chain, rung (final rung of every chain), swap_rate per
+    neighbouring pair, rung_mean_energy [n_segments, n_rungs] (mean energy on each rung at the swap points).
+    """
+    eng = engine or default_engine()
+    mode = _mode(mcmc_type)
+    betas = np.asarray(betas, dtype=np.float64)
+    K, R = len(betas), int(n_ladders)
+    if K < 2:
+        raise ValueError("parallel tempering needs at least two temperatures")
+    if swap_every % 32 != 0 or swap_every <= 0:
+        raise ValueError("swap_every must be a positive multiple of 32")
+    tabs = np.repeat(betas[:, None], n_steps, axis=1)               # constant schedule per rung
+    nc = K * R
+    ladder = np.repeat(np.arange(R), K)                             # chain -> ladder
+    rung = np.tile(np.arange(K, dtype=np.int32), R)                 # chain -> rung (changes at swaps)
+    seeds = (base_seed + np.arange(nc)).astype(np.uint64)
+    rng = np.random.RandomState(swap_seed)
+    tried = np.zeros(K - 1, dtype=np.int64)
+    done = np.zeros(K - 1, dtype=np.int64)
+    means, res, t, seg = [], None, 0, 0
+    while t < n_steps or res is None:
+        stop = min(n_steps, t + swap_every)
+        res = eng.run(mode, N, n_steps, seeds, tabs, groups=rung.copy(), init_mode=init_mode, history="none",
+                      resume=res, stop_step=stop if stop < n_steps else None)
+        t = stop
+        e = np.asarray(res.final_energy, dtype=np.int64)
+        means.append(np.bincount(rung, weights=e, minlength=K) / R)
+        if t >= n_steps:
+            break
+        # chain sitting on rung r of each ladder
+        at = np.empty((R, K), dtype=np.int64)
+        at[ladder, rung] = np.arange(nc)
+        for r in range(seg % 2, K - 1, 2):
+            a, b = at[:, r], at[:, r + 1]
+            log_p = (betas[r] - betas[r + 1]) * (e[a] - e[b])
+            swap = np.log(rng.random_sample(R)) < log_p
+            tried[r] += R
+            done[r] += int(swap.sum())
+            rung[a[swap]], rung[b[swap]] = r + 1, r
+        seg += 1
+    return {"best_energy": np.asarray(res.best_energy), "best_state": np.asarray(res.best_state), "final_energy": np.asarray(res.final_energy),
+            "rung": rung, "ladder": ladder, "swap_rate": done / np.maximum(tried, 1), "rung_mean_energy": np.array(means),
+            "betas": betas, "n_accepted": np.asarray(res.n_accepted)}

@@ -104,3 +104,29 @@ def test_competition_flow(mcq, engine, tmp_path):
     h = np.array([int(x.split(",")[2]) for x in lines]).reshape(9, 9)
     assert [r["best_energy"] for r in results] == sorted(r["best_energy"] for r in results)
     assert int(engine.energy("board", 9, h[None].astype(np.uint8))[0]) == results[0]["best_energy"]
+
+
+def test_parallel_tempering(mcq, engine):
+    """Replica exchange (not in the reference): bookkeeping invariants, no-swap equivalence, and the
+    point of it -- the cold rung finds lower energies than independent chains at the same temperature."""
+    import numpy as np
+    from monte_carlo_collective_b200 import drivers, schedules
+    betas = [round(float(b), 3) for b in np.linspace(2.0, 3.4, 8)]   # close enough for neighbouring rungs to overlap
+    n, ns, R = 8, 16384, 32
+    pt = drivers.parallel_tempering(n, ns, betas, n_ladders=R, swap_every=256, base_seed=7, engine=engine)
+    K = len(betas)
+    assert pt["rung_mean_energy"].shape == (ns // 256, K)
+    for lad in range(R):                                   # every ladder still has one chain per rung
+        assert sorted(pt["rung"][pt["ladder"] == lad]) == list(range(K))
+    assert ((pt["swap_rate"] > 0.05) & (pt["swap_rate"] < 0.98)).all(), pt["swap_rate"]
+    assert (np.diff(pt["rung_mean_energy"][-20:].mean(axis=0)) < 0).all()     # colder rungs sit lower
+    # swaps off (one segment longer than the run): plain independent chains with the same seeds and temperatures
+    off = drivers.parallel_tempering(n, 2048, betas, n_ladders=R, swap_every=4096, base_seed=7, engine=engine)
+    tabs = np.repeat(np.asarray(betas)[:, None], 2048, axis=1)
+    ref = engine.run("board", n, 2048, (7 + np.arange(K * R)).astype(np.uint64), tabs,
+                     groups=np.tile(np.arange(K, dtype=np.int32), R), history="none")
+    assert (off["best_energy"] == ref.best_energy).all() and (off["best_state"] == ref.best_state).all()
+    # against independent chains held at the coldest temperature for the same number of steps
+    cold = engine.run("board", n, ns, (1000 + np.arange(K * R)).astype(np.uint64), np.full((1, ns), betas[-1]), history="none")
+    assert pt["best_energy"].min() <= cold.best_energy.min() + 2
+    assert np.sort(pt["best_energy"])[: R].mean() < np.sort(cold.best_energy)[: R].mean() + 1.0
