@@ -399,18 +399,28 @@ static cudaError_t launch_spec_lpc(const KArgs &a, bool replay, int grid, int bl
     return replay ? launch_spec_one<false, true, false, 0, LPC>(a, grid, block, smem, s) : launch_spec_nr<false, LPC>(a, grid, block, smem, s);
 }
 
-template <bool FULL, bool EARLY>
+template <bool FULL, bool EARLY, int NT>
 static cudaError_t launch_wide_one(const KArgs &a, int grid, size_t smem, cudaStream_t s) {
-    auto k = wide_kernel<FULL, EARLY>;
+    auto k = wide_kernel<FULL, EARLY, NT>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin);
     if (e != cudaSuccess) return e;
-    k<<<grid, WIDE_THREADS, smem, s>>>(a);
+    k<<<grid, NT, smem, s>>>(a);
     return cudaGetLastError();
 }
 
-static cudaError_t launch_wide(const KArgs &a, int grid, size_t smem, cudaStream_t s) {
-    if (a.full) return launch_wide_one<true, false>(a, grid, smem, s);
-    return a.patience >= 0 ? launch_wide_one<false, true>(a, grid, smem, s) : launch_wide_one<false, false>(a, grid, smem, s);
+template <int NT>
+static cudaError_t launch_wide_nt(const KArgs &a, int grid, size_t smem, cudaStream_t s) {
+    if (a.full) return launch_wide_one<true, false, NT>(a, grid, smem, s);
+    return a.patience >= 0 ? launch_wide_one<false, true, NT>(a, grid, smem, s) : launch_wide_one<false, false, NT>(a, grid, smem, s);
+}
+
+static cudaError_t launch_wide(int threads, const KArgs &a, int grid, size_t smem, cudaStream_t s) {
+    switch (threads) {
+        case 32: return launch_wide_nt<32>(a, grid, smem, s);
+        case 64: return launch_wide_nt<64>(a, grid, smem, s);
+        case 128: return launch_wide_nt<128>(a, grid, smem, s);
+        default: return launch_wide_nt<256>(a, grid, smem, s);
+    }
 }
 
 static cudaError_t launch_spec(int lpc, const KArgs &a, bool replay, int grid, int block, size_t smem, cudaStream_t s) {
@@ -690,7 +700,7 @@ int mcq_run(mcq_ctx *ctx, const mcq_run_params *p) {
     if (use_wide && replay) return fail(MCQ_EINVAL, "MCQ_ALGO_WIDE does not replay recorded streams");
     {
         const Layout l1 = make_layout(full, p->n, p->q, 1);
-        const size_t need = (size_t)l1.off_pkt + round_up(l1.off_occ - l1.off_state, 16) + WIDE_RING * 16 + WIDE_XCH_BYTES;
+        const size_t need = (size_t)l1.off_pkt + round_up(l1.off_occ - l1.off_state, 16) + 2 * 32 * 16 + WIDE_XCH_BYTES;   // narrowest CTA
         if (p->algo == MCQ_ALGO_AUTO && !use_spec && !replay && G == 0 && need <= smem_block &&
             !(use_gmem && nc >= 32 * ctx->prop.multiProcessorCount && ns < 1000000))
             use_wide = true;
@@ -702,9 +712,28 @@ int mcq_run(mcq_ctx *ctx, const mcq_run_params *p) {
         while (G < 32 && (size_t)make_layout(full, p->n, p->q, G).stride * (32 / G) > smem_block) G *= 2;
     }
     Layout lay = make_layout(full, p->n, p->q, G);
-    const int w_best = lay.off_pkt, w_ring = w_best + round_up(lay.off_occ - lay.off_state, 16), w_xch = w_ring + WIDE_RING * 16;
-    const size_t wide_smem = (size_t)w_xch + WIDE_XCH_BYTES;
-    if (use_wide && wide_smem > smem_block) return fail(MCQ_ENOMEM, "the line counters of one chain do not fit in shared memory");
+    // CTA-per-chain kernel: 8, 4, 2 or 1 warps per chain.  A round is bound by its dependent instruction chain, so what
+    // counts is how many chains an SM holds (shared memory: counters + state + a ring of 2 * threads steps;
+    // registers: 128 per thread); among equals the widest CTA speculates furthest.  warps_per_cta = 1, 2, 4, 8 overrides.
+    const int w_best = lay.off_pkt, w_ring = w_best + round_up(lay.off_occ - lay.off_state, 16);
+    int wide_threads = WIDE_THREADS;
+    auto wide_bytes = [&](int nt) { return (size_t)w_ring + 2 * (size_t)nt * 16 + WIDE_XCH_BYTES; };
+    if (use_wide) {
+        const long long want = (nc + ctx->prop.multiProcessorCount - 1) / ctx->prop.multiProcessorCount;   // chains per SM on offer
+        long long best_conc = 0;
+        for (int nt = 256; nt >= 32; nt >>= 1) {
+            if (wide_bytes(nt) > smem_block) continue;
+            const long long by_smem = (long long)(smem_sm / (wide_bytes(nt) + 1024)), by_regs = 65536 / (128 * nt);
+            const long long conc = std::min(want, std::min<long long>(32, std::min(by_smem, by_regs)));
+            if (conc > best_conc) { best_conc = conc; wide_threads = nt; }
+        }
+        if (best_conc == 0) return fail(MCQ_ENOMEM, "the line counters of one chain do not fit in shared memory");
+        if (p->warps_per_cta == 1 || p->warps_per_cta == 2 || p->warps_per_cta == 4 || p->warps_per_cta == 8) wide_threads = p->warps_per_cta * 32;
+        if (const char *e = getenv("MCQ_WIDE_THREADS")) { const int v = atoi(e); if (v == 32 || v == 64 || v == 128 || v == 256) wide_threads = v; }
+        if (wide_bytes(wide_threads) > smem_block) return fail(MCQ_ENOMEM, "the line counters of one chain do not fit in shared memory at this CTA width");
+    }
+    const int w_xch = w_ring + 2 * wide_threads * 16;
+    const size_t wide_smem = wide_bytes(wide_threads);
     if (!use_gmem && !use_wide && (size_t)lay.stride * (32 / G) > smem_block) return fail(MCQ_ENOMEM, "a warp's chains do not fit in shared memory; raise lanes_per_chain");
     int wpc = p->warps_per_cta;
     if (wpc < 0 || wpc > 8) return fail(MCQ_EINVAL, "warps_per_cta must be in [0, 8]");
@@ -720,7 +749,7 @@ int mcq_run(mcq_ctx *ctx, const mcq_run_params *p) {
     }
     if (best_chains == 0 && !use_gmem && !use_wide) return fail(MCQ_ENOMEM, "requested warps_per_cta does not fit in shared memory");
     int cpc = use_gmem ? 128 : use_wide ? 1 : best_w * 32 / G;
-    int block = use_gmem ? 128 : use_wide ? WIDE_THREADS : best_w * 32;
+    int block = use_gmem ? 128 : use_wide ? wide_threads : best_w * 32;
     int grid = (nc + cpc - 1) / cpc;
     size_t smem = use_gmem ? 0 : use_wide ? wide_smem : (size_t)cpc * lay.stride;
     const SLayout sl = make_spec_layout(full, p->n, p->q);
@@ -1002,7 +1031,7 @@ int mcq_run(mcq_ctx *ctx, const mcq_run_params *p) {
             cudaStream_t sb = sub_stream[b];
             a.chain_begin = lo; a.n_chains = hi;
             CUDA_TRY(use_spec ? launch_spec(spec_lpc, a, replay, cta_hi - cta_lo, block, smem, sb)
-                     : use_wide ? launch_wide(a, cta_hi - cta_lo, smem, sb)
+                     : use_wide ? launch_wide(wide_threads, a, cta_hi - cta_lo, smem, sb)
                                 : launch_anneal(G, a, replay, cta_hi - cta_lo, block, smem, sb));
             ++launches;
             if (want_stats && n_cols > 0) {

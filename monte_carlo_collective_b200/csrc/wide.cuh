@@ -26,15 +26,15 @@
 
 namespace mcq {
 
-constexpr int WIDE_THREADS = 256;
-constexpr int WIDE_RING = 2 * WIDE_THREADS;   // steps of random words kept per chain
+constexpr int WIDE_THREADS = 256;             // widest CTA (one per SM on the largest boards); 128 and 64 where more CTAs fit
+// (the ring of random words keeps 2 * blockDim steps)
 constexpr int WIDE_JCAP = 62;                 // journal of state elements changed since the last best-state snapshot
 constexpr int WIDE_XCH_BYTES = 256;           // exchange words (3 per warp), journal count, journal
 
-template <bool FULL, bool EARLY>
-__global__ void __launch_bounds__(WIDE_THREADS, 1) wide_kernel(const __grid_constant__ KArgs a) {
+template <bool FULL, bool EARLY, int NT>
+__global__ void __launch_bounds__(NT, 1) wide_kernel(const __grid_constant__ KArgs a) {
     constexpr unsigned FULLMASK = 0xffffffffu;
-    constexpr int NT = WIDE_THREADS, NW = NT / 32;
+    constexpr int NW = NT / 32, RING = 2 * NT;
     constexpr int F0 = FULL ? 0 : 1;              // board mode has no (i,j) column family
     constexpr int NONE = 0x7fffffff;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) wide_kernel(const __grid_cons
     int bin = a.bin_at_begin;
     int next_edge = a.n_bins > 0 ? a.bin_starts[bin + 1] : NONE;
     int tfill = t;
-    int width = 64;   // threads that evaluate a step this round (whole warps)
+    int width = NT < 64 ? NT : 64;   // threads that evaluate a step this round (whole warps)
     unsigned char *hrow = static_cast<unsigned char *>(a.hist) +
                           ((long long)chain * a.hist_pitch - a.h_origin) * (a.hist_kind == 1 ? 2 : 4);
     uint32_t *abits_row = a.abits ? a.abits + (size_t)chain * a.abits_pitch : nullptr;
@@ -140,14 +140,14 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) wide_kernel(const __grid_cons
         // ---------------- random words: refill the ring when this round would read past it ----------------
         if (tfill < t + NT) {
             const Philox4 w = philox4x32_10((uint32_t)(tfill + tid), 0u, 0u, PHILOX_DOMAIN_STEP, key0, key1);
-            ring[(tfill + tid) & (WIDE_RING - 1)] = make_uint4(w.x, w.y, w.z, w.w);
+            ring[(tfill + tid) & (RING - 1)] = make_uint4(w.x, w.y, w.z, w.w);
             tfill += NT;
             __syncthreads();
         }
         const int rem = min(a.t_end - t, width);
         const bool valid = tid < rem;
         const int s = min(t + tid, a.t_end - 1);          // threads past the end redo the last step, masked below
-        const uint4 w = ring[s & (WIDE_RING - 1)];
+        const uint4 w = ring[s & (RING - 1)];
         const float cb = __ldg(beta_row + s);
 
         // ---------------- this thread's proposal: step s against the current state ----------------
@@ -289,8 +289,8 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) wide_kernel(const __grid_cons
                     snap = true;
                     const int jn = *jcount;
                     if (jn <= WIDE_JCAP) {
-                        if (tid < jn) {
-                            const int el = jrn[tid];
+                        for (int e = tid; e < jn; e += NT) {
+                            const int el = jrn[e];
                             if constexpr (FULL) store_pos(bst, pos32, el, load_pos(st, pos32, el));
                             else bst[el] = st[el];
                         }

@@ -136,3 +136,18 @@ if which == "widelong":
 
 if which == "wideprof2":
     run("wideprof2", "board", 64, 148, 1000000, algo="wide")
+
+if which == "wident":
+    for nt in ("256", "128", "64"):
+        os.environ["MCQ_WIDE_THREADS"] = nt
+        run("wident" + nt, "board", 30, 2368, 100000, algo="wide")
+        run("wident" + nt, "board", 40, 1184, 100000, algo="wide")
+        run("wident" + nt, "board", 64, 148, 300000, algo="wide")
+        run("wident" + nt, "full_3d", 24, 1184, 100000, algo="wide")
+
+if which == "wideauto":
+    os.environ.pop("MCQ_WIDE_THREADS", None)
+    for mode, n, nc, ns in (("board", 30, 2368, 100000), ("board", 30, 148, 100000), ("board", 40, 1184, 100000), ("board", 64, 148, 300000),
+                            ("full_3d", 24, 1184, 100000), ("full_3d", 40, 1184, 50000), ("board", 22, 4736, 100000)):
+        run("wideauto", mode, n, nc, ns)
+    run("wideauto-lines", "board", 22, 4736, 100000, algo="lines")

@@ -113,7 +113,8 @@ def test_cta_per_chain_kernel_on_large_boards(engine, mode, n):
     seeds = np.arange(nc, dtype=np.uint64) * 11 + 5
     base = engine.run(mode, n, ns, seeds, betas, groups=groups, history="full", accept_bits=True, n_bins=50, algo="gmem")
     _check_invariants(engine, mode, n, base)
-    for kw in (dict(), dict(chunk_steps=256), dict(chunk_steps=1000)):
+    for kw in (dict(), dict(chunk_steps=256), dict(chunk_steps=1000), dict(warps_per_cta=1), dict(warps_per_cta=2), dict(warps_per_cta=4, chunk_steps=512),
+               dict(warps_per_cta=8)):
         r = engine.run(mode, n, ns, seeds, betas, groups=groups, history="full", accept_bits=True, n_bins=50, algo="wide", **kw)
         for name in ("energy_history", "initial_energy", "final_energy", "best_energy", "steps_to_best", "n_accepted", "steps_done",
                      "final_state", "best_state", "accept_bits", "accept_hist"):
