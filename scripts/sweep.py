@@ -151,3 +151,9 @@ if which == "wideauto":
                             ("full_3d", 24, 1184, 100000), ("full_3d", 40, 1184, 50000), ("board", 22, 4736, 100000)):
         run("wideauto", mode, n, nc, ns)
     run("wideauto-lines", "board", 22, 4736, 100000, algo="lines")
+
+if which == "tablewide":
+    for mode in ("board", "full_3d"):
+        for n in (12, 16, 20):
+            for algo in ("table", "wide"):
+                run("tablewide", mode, n, 8192, 50000, algo=algo)
