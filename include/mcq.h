@@ -56,7 +56,7 @@ extern "C" {
 #define MCQ_HIST_I32 2
 
 /* delta-E data structure / kernel */
-#define MCQ_ALGO_AUTO 0   /* conflict table when its entries suffice (N <= 20 / 21), else one CTA per chain on line counters;
+#define MCQ_ALGO_AUTO 0   /* conflict table up to N = 18 (full_3d) / 21 (board), else one CTA per chain on line counters;
                              replays and short runs of very many large-board chains use LINES / GMEM */
 #define MCQ_ALGO_LINES 1  /* per-line occupancy counters, `lanes_per_chain` lanes per chain (anneal.cuh) */
 #define MCQ_ALGO_TABLE 2  /* per-cell conflict table, one warp per chain, speculative rounds (spec.cuh) */

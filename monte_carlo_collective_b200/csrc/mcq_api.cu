@@ -686,7 +686,9 @@ int mcq_run(mcq_ctx *ctx, const mcq_run_params *p) {
     if (G != 0 && G != 4 && G != 8 && G != 16 && G != 32) return fail(MCQ_EINVAL, "lanes_per_chain must be 0, 4, 8, 16 or 32");
     if (p->algo < MCQ_ALGO_AUTO || p->algo > MCQ_ALGO_WIDE) return fail(MCQ_EINVAL, "unknown algo");
     if (p->algo == MCQ_ALGO_TABLE && !spec_eligible(full, p->n)) return fail(MCQ_EINVAL, "MCQ_ALGO_TABLE serves N <= 20 (full_3d) or N <= 21 (board)");
-    const bool use_spec = p->algo == MCQ_ALGO_TABLE || (p->algo == MCQ_ALGO_AUTO && G == 0 && spec_eligible(full, p->n));
+    // full_3d N = 19, 20: the 16-bit table leaves few chains per SM; the CTA-per-chain kernel is 11-24 % ahead (measured)
+    const bool table_pays = spec_eligible(full, p->n) && !(full && p->n >= 19 && !replay);
+    const bool use_spec = p->algo == MCQ_ALGO_TABLE || (p->algo == MCQ_ALGO_AUTO && G == 0 && table_pays);
     // Boards whose line counters leave room for only a few chains per SM run one thread per chain with the
     // counters in global memory (HBM-bound byte traffic instead of a latency-bound handful of warps).
     bool use_gmem = !use_spec && (p->algo == MCQ_ALGO_GMEM ||

@@ -1,6 +1,6 @@
 // Speculative CTA-per-chain annealing kernel on line counters (sm_100a): the large-board path.
 //
-// Boards beyond the conflict-table kernel (N > 20 full_3d, N > 21 board; C5 is N = 64 with 4096 queens)
+// Boards beyond the conflict-table kernel (N > 18 full_3d, N > 21 board; C5 is N = 64 with 4096 queens)
 // keep one uint8 counter per attack line (anneal.cuh) -- 121 KB at N = 64, i.e. ONE chain per SM.  A single
 // warp stepping through such a chain is latency-bound, and one thread per chain with the counters in
 // global memory (anneal_kernel<1> + gslab) is bound by 25 random HBM sectors per proposal.  Here the whole

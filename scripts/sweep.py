@@ -157,3 +157,11 @@ if which == "tablewide":
         for n in (12, 16, 20):
             for algo in ("table", "wide"):
                 run("tablewide", mode, n, 8192, 50000, algo=algo)
+
+if which == "tablewide2":
+    for n in (17, 18, 19, 20):
+        for algo in ("table", "wide"):
+            run("tablewide2", "full_3d", n, 8192, 50000, algo=algo)
+    for n in (20, 21):
+        for algo in ("table", "wide"):
+            run("tablewide2", "board", n, 16384, 50000, algo=algo)
