@@ -35,6 +35,8 @@ template <bool FULL, bool EARLY, int NT>
 __global__ void __launch_bounds__(NT, 1) wide_kernel(const __grid_constant__ KArgs a) {
     constexpr unsigned FULLMASK = 0xffffffffu;
     constexpr int NW = NT / 32, RING = 2 * NT;
+    // a single-warp CTA needs no block barrier and no exchange through shared memory
+    auto cta_sync = [] { if constexpr (NT == 32) __syncwarp(); else __syncthreads(); };
     constexpr int F0 = FULL ? 0 : 1;              // board mode has no (i,j) column family
     constexpr int NONE = 0x7fffffff;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -142,7 +144,7 @@ __global__ void __launch_bounds__(NT, 1) wide_kernel(const __grid_constant__ KAr
             const Philox4 w = philox4x32_10((uint32_t)(tfill + tid), 0u, 0u, PHILOX_DOMAIN_STEP, key0, key1);
             ring[(tfill + tid) & (RING - 1)] = make_uint4(w.x, w.y, w.z, w.w);
             tfill += NT;
-            __syncthreads();
+            cta_sync();
         }
         const int rem = min(a.t_end - t, width);
         const bool valid = tid < rem;
@@ -211,9 +213,12 @@ __global__ void __launch_bounds__(NT, 1) wide_kernel(const __grid_constant__ KAr
         // accepting thread together with its delta-E
         const int mine = accept ? (tid << 16) | (dE + 0x8000) : NONE;
         const int wmin = __reduce_min_sync(FULLMASK, mine);
-        if (lane == 0) xch[warp] = wmin;
-        __syncthreads();
-        const int cmin = __reduce_min_sync(FULLMASK, lane < NW ? xch[lane] : NONE);
+        int cmin = wmin;
+        if constexpr (NT > 32) {
+            if (lane == 0) xch[warp] = wmin;
+            __syncthreads();
+            cmin = __reduce_min_sync(FULLMASK, lane < NW ? xch[lane] : NONE);
+        }
         int first = cmin == NONE ? -1 : cmin >> 16;
         int adv = first >= 0 ? first + 1 : rem;            // steps consumed by this round
         int adv_h = adv;                                   // steps whose energy is appended to the history
@@ -265,7 +270,7 @@ __global__ void __launch_bounds__(NT, 1) wide_kernel(const __grid_constant__ KAr
                 }
             }
         }
-        __syncthreads();   // counters and state are final before the next round (and before a snapshot) reads them
+        cta_sync();   // counters and state are final before the next round (and before a snapshot) reads them
 
         // ---------------- bookkeeping ----------------
         const int n_before = n_acc;
