@@ -92,25 +92,7 @@ static Layout make_layout(int full, int N, int Q, int G) {
     return L;
 }
 
-static SLayout make_spec_layout(int full, int N, int Q) {
-    SLayout L;
-    L.tbl = round_up((N * N * N + 1) * (full ? 2 : 1), 4);   // full_3d: uint16 entries (count | occupied << 15)
-    L.off_state = L.tbl;
-    const int state_b = full ? Q * 4 : N * N;
-    L.off_occ = round_up(L.off_state + state_b, 4);
-    const int occ_b = 0;   // the occupancy flag lives in the table entries
-    L.off_rec = L.off_occ + occ_b;
-    L.off_ring = round_up(L.off_rec + 8 * 4, 16);
-    L.stride = L.off_ring + 64 * 16;
-    L.nbr_len = round_up((full ? NFAM : NFAM - 1) * (N - 1) + 1, 32);   // the cell itself + its line neighbours
-    L.rounds = L.nbr_len / 32;
-    const int W = 2 * N - 1;
-    const int lut_bytes = (W * W * W + 31) / 32 * 4;
-    L.wide_bias = (N - 1) * (W * W + W + 1);
-    L.off_wide = full ? lut_bytes : 0;
-    L.cta_bytes = full ? round_up(lut_bytes + N * N * N * 2, 16) : 0;
-    return L;
-}
+static SLayout make_spec_layout(int full, int N, int Q) { return spec_layout(full, N, Q); }
 
 // board: uint8 entries hold at most 12*N; full_3d: uint16 entries, bounded by the neighbour-row length
 // the kernels are compiled for (13*(N-1) <= 256) and the 16-bit cell / wide ids
@@ -366,9 +348,9 @@ static cudaError_t launch_g(const KArgs &a, bool replay, int grid, int block, si
     return replay ? launch_one<G, false, true>(a, grid, block, smem, s) : launch_one<G, false, false>(a, grid, block, smem, s);
 }
 
-template <bool FULL, bool REPLAY, bool EARLY, int NR, int LPC>
+template <bool FULL, bool REPLAY, bool EARLY, int NR, int LPC, int CN = 0>
 static cudaError_t launch_spec_one(const KArgs &a, int grid, int block, size_t smem, cudaStream_t s) {
-    auto k = spec_kernel<FULL, REPLAY, EARLY, NR, LPC>;
+    auto k = spec_kernel<FULL, REPLAY, EARLY, NR, LPC, CN>;
     // always the device maximum: the attribute is per function and per device, so concurrent host threads
     // (one engine each) must not race different values into it
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin);
@@ -377,9 +359,32 @@ static cudaError_t launch_spec_one(const KArgs &a, int grid, int block, size_t s
     return cudaGetLastError();
 }
 
+// the board sizes the reference's experiments use are compiled in altogether (N, Q = N^2 and the slab geometry
+// become immediates: ~25 fewer instructions per round); other sizes take the geometry from the arguments
+template <bool FULL, int CN>
+static cudaError_t launch_spec_cn(const KArgs &a, int grid, int block, size_t smem, cudaStream_t s) {
+    constexpr int NR = spec_layout(FULL, CN, CN * CN).rounds;
+    return launch_spec_one<FULL, false, false, NR, 32, CN>(a, grid, block, smem, s);
+}
+
 // production kernels have the neighbour-row length compiled in; replay / early-stop ones take it at run time
 template <bool FULL, int LPC>
 static cudaError_t launch_spec_nr(const KArgs &a, int grid, int block, size_t smem, cudaStream_t s) {
+    if (LPC == 32 && a.Q == a.N * a.N && !getenv("MCQ_NO_FIXED_N")) {
+        switch (a.N) {
+            case 8: return launch_spec_cn<FULL, 8>(a, grid, block, smem, s);
+            case 9: return launch_spec_cn<FULL, 9>(a, grid, block, smem, s);
+            case 10: return launch_spec_cn<FULL, 10>(a, grid, block, smem, s);
+            case 11: return launch_spec_cn<FULL, 11>(a, grid, block, smem, s);
+            case 12: return launch_spec_cn<FULL, 12>(a, grid, block, smem, s);
+            case 13: return launch_spec_cn<FULL, 13>(a, grid, block, smem, s);
+            case 14: return launch_spec_cn<FULL, 14>(a, grid, block, smem, s);
+            case 15: return launch_spec_cn<FULL, 15>(a, grid, block, smem, s);
+            case 16: return launch_spec_cn<FULL, 16>(a, grid, block, smem, s);
+            case 20: if (!FULL) return launch_spec_cn<false, 20>(a, grid, block, smem, s); break;
+            default: break;
+        }
+    }
     switch (a.sl.rounds) {
         case 1: return launch_spec_one<FULL, false, false, 1, LPC>(a, grid, block, smem, s);
         case 2: return launch_spec_one<FULL, false, false, 2, LPC>(a, grid, block, smem, s);

@@ -39,7 +39,42 @@ namespace mcq {
 #ifndef MCQ_SPEC_MINB
 #define MCQ_SPEC_MINB 7   // min CTAs (of 4 warps) per SM the register allocation must allow
 #endif
-constexpr int MAX_NBR_ROUNDS = 8;   // 13*(N-1) <= 256 for every N the uint8 table admits
+constexpr int MAX_NBR_ROUNDS = 8;
+
+// Slab geometry of the conflict-table kernel.  constexpr: the host computes it per call, and kernels compiled
+// for a fixed board size (template parameter CN) fold it into immediates.
+__host__ __device__ constexpr int spec_round_up(int x, int m) { return (x + m - 1) / m * m; }
+__host__ __device__ constexpr SLayout spec_layout(int full, int N, int Q) {
+    SLayout L{};
+    L.tbl = spec_round_up((N * N * N + 1) * (full ? 2 : 1), 4);   // full_3d: uint16 entries (count | occupied << 15)
+    L.off_state = L.tbl;
+    const int state_b = full ? Q * 4 : N * N;
+    L.off_occ = spec_round_up(L.off_state + state_b, 4);          // (the occupancy flag lives in the table entries)
+    L.off_rec = L.off_occ;
+    L.off_ring = spec_round_up(L.off_rec + 8 * 4, 16);
+    L.stride = L.off_ring + 64 * 16;
+    L.nbr_len = spec_round_up((full ? NFAM : NFAM - 1) * (N - 1) + 1, 32);   // the cell itself + its line neighbours
+    L.rounds = L.nbr_len / 32;
+    const int W = 2 * N - 1;
+    const int lut_bytes = (W * W * W + 31) / 32 * 4;
+    L.wide_bias = (N - 1) * (W * W + W + 1);
+    L.off_wide = full ? lut_bytes : 0;
+    L.cta_bytes = full ? spec_round_up(lut_bytes + N * N * N * 2, 16) : 0;
+    return L;
+}
+// CN > 0: board size (and Q = N^2) known at compile time; CN == 0: taken from the kernel arguments
+template <bool FULL, int CN>
+struct SpecGeom {
+    static __device__ __forceinline__ constexpr SLayout layout(const KArgs &) { return spec_layout(FULL, CN, CN * CN); }
+    static __device__ __forceinline__ constexpr int n(const KArgs &) { return CN; }
+    static __device__ __forceinline__ constexpr int q(const KArgs &) { return CN * CN; }
+};
+template <bool FULL>
+struct SpecGeom<FULL, 0> {
+    static __device__ __forceinline__ SLayout layout(const KArgs &a) { return a.sl; }
+    static __device__ __forceinline__ int n(const KArgs &a) { return a.N; }
+    static __device__ __forceinline__ int q(const KArgs &a) { return a.Q; }
+};   // 13*(N-1) <= 256 for every N the uint8 table admits
 
 // direction of the attack line of family f (same family order as make_coefs / line_ids);
 // the first non-zero component is always +1
@@ -242,7 +277,7 @@ __device__ __forceinline__ float ex2_approx(float x) {
 // groups waste fewer evaluated proposals per round (at 3 % acceptance a 16-lane group commits
 // 12.9 of 16, a 32-lane group 20.7 of 32); committed moves are applied by the whole warp, one
 // chain after the other, so the table update keeps 32 lanes busy either way.
-template <bool FULL, bool REPLAY, bool EARLY, int NR, int LPC>
+template <bool FULL, bool REPLAY, bool EARLY, int NR, int LPC, int CN = 0>
 __global__ void __launch_bounds__(128, MCQ_SPEC_MINB) spec_kernel(const __grid_constant__ KArgs a) {
     constexpr unsigned FULLMASK = 0xffffffffu;
     constexpr int NF = FULL ? NFAM : NFAM - 1;
@@ -258,11 +293,13 @@ __global__ void __launch_bounds__(128, MCQ_SPEC_MINB) spec_kernel(const __grid_c
     // keep both in registers: the compiler otherwise re-derives them (S2R + address-window arithmetic) every round
     asm volatile("" : "+r"(lane), "+r"(sbase));
     const int sub = lane & (LPC - 1), half = LPC == 32 ? 0 : lane / LPC;
-    const int N = a.N;
+    const int N = SpecGeom<FULL, CN>::n(a), Q = SpecGeom<FULL, CN>::q(a);
+    const SLayout sl = SpecGeom<FULL, CN>::layout(a);
+    const int state_bytes = FULL ? 3 * Q : Q;
 
     // ---- CTA-shared geometry: shared-line bits at offset 0, cell -> wide id at sl.off_wide ----
     if (FULL) {
-        for (int w = threadIdx.x; w < a.sl.cta_bytes / 4; w += blockDim.x) SM32(4 * w) = __ldg(a.geo + w);
+        for (int w = threadIdx.x; w < sl.cta_bytes / 4; w += blockDim.x) SM32(4 * w) = __ldg(a.geo + w);
         __syncthreads();
     }
     const int slab0 = (int)(threadIdx.x >> 5) * CPW;                      // first slab of this warp
@@ -272,11 +309,11 @@ __global__ void __launch_bounds__(128, MCQ_SPEC_MINB) spec_kernel(const __grid_c
     const bool live = chain < a.n_chains;
     const int chain_c = live ? chain : chain0;                            // for pointer set-up only
 
-    const int sT = a.sl.cta_bytes + (slab0 + half) * a.sl.stride;   // table T[N^3 + 1]
-    const int sP = sT + a.sl.off_state;   // board: heights u8; full_3d: u32 per queen = cell id | wide id << 16
-    const int sW = a.sl.off_wide;
-    const int L = a.sl.nbr_len, rounds = a.sl.rounds;
-    const uint32_t wide_bias = (uint32_t)a.sl.wide_bias;   // (N-1)*(W^2+W+1): centres the wide-id difference in the LUT
+    const int sT = sl.cta_bytes + (slab0 + half) * sl.stride;   // table T[N^3 + 1]
+    const int sP = sT + sl.off_state;   // board: heights u8; full_3d: u32 per queen = cell id | wide id << 16
+    const int sW = sl.off_wide;
+    const int L = sl.nbr_len, rounds = sl.rounds;
+    const uint32_t wide_bias = (uint32_t)sl.wide_bias;   // (N-1)*(W^2+W+1): centres the wide-id difference in the LUT
 
     const uint16_t *nbr_lane = a.nbr + lane;   // this lane's column of the neighbour rows
     // what a queen adds to the entry of her own cell (slot 0 of the cell's row, i.e. lane 0's first entry):
@@ -286,12 +323,12 @@ __global__ void __launch_bounds__(128, MCQ_SPEC_MINB) spec_kernel(const __grid_c
     // ---- build the slabs from the external states: one chain at a time, all 32 lanes ----
     int E = 0;
     for (int h = 0; h < CPW; ++h) {
-        const int bT = a.sl.cta_bytes + (slab0 + h) * a.sl.stride, bP = bT + a.sl.off_state;
-        for (int w = lane; w < a.sl.stride / 4; w += 32) SM32(bT + 4 * w) = 0u;
+        const int bT = sl.cta_bytes + (slab0 + h) * sl.stride, bP = bT + sl.off_state;
+        for (int w = lane; w < sl.stride / 4; w += 32) SM32(bT + 4 * w) = 0u;
         __syncwarp();
         if (chain0 + h >= a.n_chains) continue;   // no chain: the slab stays zero (harmless to evaluate)
-        const uint8_t *ext = a.state + (size_t)(chain0 + h) * a.state_bytes;
-        for (int qi = lane; qi < a.Q; qi += 32) {
+        const uint8_t *ext = a.state + (size_t)(chain0 + h) * state_bytes;
+        for (int qi = lane; qi < Q; qi += 32) {
             if (FULL) {
                 const int cid = ((int)ext[3 * qi] * N + (int)ext[3 * qi + 1]) * N + (int)ext[3 * qi + 2];
                 SM32(bP + 4 * qi) = (uint32_t)cid | ((uint32_t)SM16(sW + 2 * cid) << 16);
@@ -300,13 +337,13 @@ __global__ void __launch_bounds__(128, MCQ_SPEC_MINB) spec_kernel(const __grid_c
             }
         }
         __syncwarp();
-        for (int qi = 0; qi < a.Q; ++qi) {
+        for (int qi = 0; qi < Q; ++qi) {
             const int c = FULL ? (int)(SM32(bP + 4 * qi) & 0xffffu) : qi * N + (int)SM8(bP + qi);
             table_lines_add<NR, TE>(sbase + (uint32_t)bT, ptr_mad(nbr_lane, (uint32_t)c, 2u * (uint32_t)L), rounds, 1u, d0);
             __syncwarp();
         }
         int e = 0;
-        for (int qi = lane; qi < a.Q; qi += 32) {
+        for (int qi = lane; qi < Q; qi += 32) {
             const int c = FULL ? (int)(SM32(bP + 4 * qi) & 0xffffu) : qi * N + (int)SM8(bP + qi);
             e += ((int)(TE)TBL(bT, c) & CNT) - 1;
         }
@@ -344,7 +381,7 @@ __global__ void __launch_bounds__(128, MCQ_SPEC_MINB) spec_kernel(const __grid_c
     const double *un_row = REPLAY ? a.runif + (size_t)chain_c * a.n_steps : nullptr;
     int bin = a.bin_at_begin;
     int next_edge = a.n_bins > 0 ? a.bin_starts[bin + 1] : 0x7fffffff;
-    const int sG = sT + a.sl.off_ring;   // ring of random words: 64 steps x 16 B
+    const int sG = sT + sl.off_ring;   // ring of random words: 64 steps x 16 B
     [[maybe_unused]] int tfill = t;       // steps < tfill of this chain have their words in the ring
     [[maybe_unused]] uint32_t near = 0u;
     // history row, addressed by history index h = step + 1 (h_origin = index held by column 0)
@@ -369,7 +406,7 @@ __global__ void __launch_bounds__(128, MCQ_SPEC_MINB) spec_kernel(const __grid_c
             if (FULL) {
                 uint32_t q = mv & 0xfff;
                 const uint32_t i1 = (mv >> 12) & 63, j1 = (mv >> 18) & 63, k1 = (mv >> 24) & 63;
-                bad = q >= (uint32_t)a.Q || i1 >= (uint32_t)N || j1 >= (uint32_t)N || k1 >= (uint32_t)N;
+                bad = q >= (uint32_t)Q || i1 >= (uint32_t)N || j1 >= (uint32_t)N || k1 >= (uint32_t)N;
                 c1 = bad ? 0u : (i1 * N + j1) * N + k1;
                 if (bad) q = 0;
                 const int v1 = (int)(TE)TBL(sT, c1);
@@ -409,7 +446,7 @@ __global__ void __launch_bounds__(128, MCQ_SPEC_MINB) spec_kernel(const __grid_c
                          : "r"(sbase + (uint32_t)(sG + 16 * (s & 63))));
             if (FULL) {
                 const uint32_t N3 = (uint32_t)(N * N * N);
-                const uint32_t q = __umulhi(r.x, (uint32_t)a.Q);
+                const uint32_t q = __umulhi(r.x, (uint32_t)Q);
                 const uint32_t p0 = SM32(sP + 4 * q);
                 // uniform over the empty cells: redraw while occupied (the queen's own cell counts,
                 // experiments.py:226-231).  mulhi(word, N^3) == the (i,j,k) digits of anneal_kernel.
@@ -422,7 +459,7 @@ __global__ void __launch_bounds__(128, MCQ_SPEC_MINB) spec_kernel(const __grid_c
                 if (v1 & OCC) {
                     // third candidate: what is left of word x after the queen draw (its next mixed-radix
                     // digit), so that only (Q/N^3)^3 of the proposals pay for another Philox call
-                    c1 = __umulhi(r.x * (uint32_t)a.Q, N3);
+                    c1 = __umulhi(r.x * (uint32_t)Q, N3);
                     v1 = (int)(TE)TBL(sT, c1);
                     int e = 0;
                     while (v1 & OCC) {
@@ -510,7 +547,7 @@ __global__ void __launch_bounds__(128, MCQ_SPEC_MINB) spec_kernel(const __grid_c
             int bT = sT;
             if constexpr (CPW > 1) {
                 bc0 = __shfl_sync(FULLMASK, wc0, hl); bc1 = __shfl_sync(FULLMASK, wc1, hl); baux = __shfl_sync(FULLMASK, waux, hl);
-                bT = a.sl.cta_bytes + (slab0 + hl / LPC) * a.sl.stride;
+                bT = sl.cta_bytes + (slab0 + hl / LPC) * sl.stride;
             }
             const uint32_t aT = sbase + (uint32_t)bT;
             if constexpr (NR > 0) {
@@ -539,7 +576,7 @@ __global__ void __launch_bounds__(128, MCQ_SPEC_MINB) spec_kernel(const __grid_c
             }
             // the moved queen's new position (lane 0 only; a predicated store, not a branch)
             {
-                const uint32_t aP = aT + (uint32_t)a.sl.off_state;
+                const uint32_t aP = aT + (uint32_t)sl.off_state;
                 if (FULL) {
                     if (lane == 0) SM32X(aP + 4 * (baux & 0xffffu)).put(bc1 | (baux & 0xffff0000u));
                 } else {
@@ -568,14 +605,14 @@ __global__ void __launch_bounds__(128, MCQ_SPEC_MINB) spec_kernel(const __grid_c
                     // snapshot: the state at the first visit of the minimum (strict <, :252 / :340)
                     best = E;
                     if (!stop) best_step = ta + 1;
-                    uint8_t *bs = a.best_state + (size_t)chain * a.state_bytes;
+                    uint8_t *bs = a.best_state + (size_t)chain * state_bytes;
                     if (FULL) {
-                        for (int qi = sub; qi < a.Q; qi += LPC) {
+                        for (int qi = sub; qi < Q; qi += LPC) {
                             const int c = (int)(SM32(sP + 4 * qi) & 0xffffu);
                             bs[3 * qi] = (uint8_t)(c / (N * N)); bs[3 * qi + 1] = (uint8_t)((c / N) % N); bs[3 * qi + 2] = (uint8_t)(c % N);
                         }
                     } else {
-                        for (int c = sub; c < a.Q; c += LPC) bs[c] = SM8(sP + c);
+                        for (int c = sub; c < Q; c += LPC) bs[c] = SM8(sP + c);
                     }
                 }
             }
@@ -602,14 +639,14 @@ __global__ void __launch_bounds__(128, MCQ_SPEC_MINB) spec_kernel(const __grid_c
         a.steps_done[chain] = done;
         if (REPLAY && a.near_cnt) a.near_cnt[chain] += near;
     }
-    uint8_t *out = a.state + (size_t)chain * a.state_bytes;
+    uint8_t *out = a.state + (size_t)chain * state_bytes;
     if (FULL) {
-        for (int qi = sub; qi < a.Q; qi += LPC) {
+        for (int qi = sub; qi < Q; qi += LPC) {
             const int c = (int)(SM32(sP + 4 * qi) & 0xffffu);
             out[3 * qi] = (uint8_t)(c / (N * N)); out[3 * qi + 1] = (uint8_t)((c / N) % N); out[3 * qi + 2] = (uint8_t)(c % N);
         }
     } else {
-        for (int c = sub; c < a.Q; c += LPC) out[c] = SM8(sP + c);
+        for (int c = sub; c < Q; c += LPC) out[c] = SM8(sP + c);
     }
 }
 
