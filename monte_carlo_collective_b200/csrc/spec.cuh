@@ -41,9 +41,57 @@ namespace mcq {
 #endif
 constexpr int MAX_NBR_ROUNDS = 8;
 
+// direction of the attack line of family f (same family order as make_coefs / line_ids);
+// the first non-zero component is always +1
+__host__ __device__ constexpr void family_dir(int f, int &dx, int &dy, int &dz) {
+    // 2-bit fields (d+1), one base-4 digit per family, packed into immediates (no local array)
+    // dx+1 per family F0..F12: 1,1,2,2,2,2,2,1,1,2,2,2,2
+    // dy+1 per family F0..F12: 1,2,1,2,0,1,1,2,2,2,2,0,0
+    // dz+1 per family F0..F12: 2,1,1,1,1,2,0,2,0,2,0,2,0
+    constexpr unsigned long long PX = 1ull | 1ull << 2 | 2ull << 4 | 2ull << 6 | 2ull << 8 | 2ull << 10 | 2ull << 12 | 1ull << 14 |
+                                      1ull << 16 | 2ull << 18 | 2ull << 20 | 2ull << 22 | 2ull << 24;
+    constexpr unsigned long long PY = 1ull | 2ull << 2 | 1ull << 4 | 2ull << 6 | 0ull << 8 | 1ull << 10 | 1ull << 12 | 2ull << 14 |
+                                      2ull << 16 | 2ull << 18 | 2ull << 20 | 0ull << 22 | 0ull << 24;
+    constexpr unsigned long long PZ = 2ull | 1ull << 2 | 1ull << 4 | 1ull << 6 | 1ull << 8 | 2ull << 10 | 0ull << 12 | 2ull << 14 |
+                                      0ull << 16 | 2ull << 18 | 0ull << 20 | 2ull << 22 | 0ull << 24;
+    dx = (int)((PX >> (2 * f)) & 3) - 1;
+    dy = (int)((PY >> (2 * f)) & 3) - 1;
+    dz = (int)((PZ >> (2 * f)) & 3) - 1;
+}
+
 // Slab geometry of the conflict-table kernel.  constexpr: the host computes it per call, and kernels compiled
 // for a fixed board size (template parameter CN) fold it into immediates.
 __host__ __device__ constexpr int spec_round_up(int x, int m) { return (x + m - 1) / m * m; }
+// Number of entries of a cell's neighbour row: the cell itself + every other cell on its attack lines.  The
+// line through (x,y,z) along (dx,dy,dz) runs over t in [lo, hi]; each axis with d != 0 bounds t.
+__host__ __device__ constexpr int spec_row_entries(int full, int N, int x, int y, int z) {
+    int n = 1;
+    for (int f = full ? 0 : 1; f < NFAM; ++f) {
+        int d[3] = {0, 0, 0};
+        family_dir(f, d[0], d[1], d[2]);
+        const int c[3] = {x, y, z};
+        int lo = -(N - 1), hi = N - 1;
+        for (int a = 0; a < 3; ++a) {
+            if (d[a] > 0) { lo = lo > -c[a] ? lo : -c[a]; hi = hi < N - 1 - c[a] ? hi : N - 1 - c[a]; }
+            if (d[a] < 0) { lo = lo > c[a] - (N - 1) ? lo : c[a] - (N - 1); hi = hi < c[a] ? hi : c[a]; }
+        }
+        n += hi - lo;
+    }
+    return n;
+}
+// longest row of the board: the count is a sum of concave functions of the position, symmetric under the
+// reflections of the cube, so the maximum sits on the cells next to the centre
+__host__ __device__ constexpr int spec_max_row(int full, int N) {
+    int best = 0;
+    const int m = (N - 1) / 2;
+    for (int x = m; x <= N / 2; ++x)
+        for (int y = m; y <= N / 2; ++y)
+            for (int z = m; z <= N / 2; ++z) {
+                const int n = spec_row_entries(full, N, x, y, z);
+                best = n > best ? n : best;
+            }
+    return best;
+}
 __host__ __device__ constexpr SLayout spec_layout(int full, int N, int Q) {
     SLayout L{};
     L.tbl = spec_round_up((N * N * N + 1) * (full ? 2 : 1), 4);   // full_3d: uint16 entries (count | occupied << 15)
@@ -53,7 +101,7 @@ __host__ __device__ constexpr SLayout spec_layout(int full, int N, int Q) {
     L.off_rec = L.off_occ;
     L.off_ring = spec_round_up(L.off_rec + 8 * 4, 16);
     L.stride = L.off_ring + 64 * 16;
-    L.nbr_len = spec_round_up((full ? NFAM : NFAM - 1) * (N - 1) + 1, 32);   // the cell itself + its line neighbours
+    L.nbr_len = spec_round_up(spec_max_row(full, N), 32);   // the cell itself + its line neighbours, longest row
     L.rounds = L.nbr_len / 32;
     const int W = 2 * N - 1;
     const int lut_bytes = (W * W * W + 31) / 32 * 4;
@@ -75,24 +123,6 @@ struct SpecGeom<FULL, 0> {
     static __device__ __forceinline__ int n(const KArgs &a) { return a.N; }
     static __device__ __forceinline__ int q(const KArgs &a) { return a.Q; }
 };   // 13*(N-1) <= 256 for every N the uint8 table admits
-
-// direction of the attack line of family f (same family order as make_coefs / line_ids);
-// the first non-zero component is always +1
-__host__ __device__ inline void family_dir(int f, int &dx, int &dy, int &dz) {
-    // 2-bit fields (d+1), one base-4 digit per family, packed into immediates (no local array)
-    // dx+1 per family F0..F12: 1,1,2,2,2,2,2,1,1,2,2,2,2
-    // dy+1 per family F0..F12: 1,2,1,2,0,1,1,2,2,2,2,0,0
-    // dz+1 per family F0..F12: 2,1,1,1,1,2,0,2,0,2,0,2,0
-    constexpr unsigned long long PX = 1ull | 1ull << 2 | 2ull << 4 | 2ull << 6 | 2ull << 8 | 2ull << 10 | 2ull << 12 | 1ull << 14 |
-                                      1ull << 16 | 2ull << 18 | 2ull << 20 | 2ull << 22 | 2ull << 24;
-    constexpr unsigned long long PY = 1ull | 2ull << 2 | 1ull << 4 | 2ull << 6 | 0ull << 8 | 1ull << 10 | 1ull << 12 | 2ull << 14 |
-                                      2ull << 16 | 2ull << 18 | 2ull << 20 | 0ull << 22 | 0ull << 24;
-    constexpr unsigned long long PZ = 2ull | 1ull << 2 | 1ull << 4 | 1ull << 6 | 1ull << 8 | 2ull << 10 | 0ull << 12 | 2ull << 14 |
-                                      0ull << 16 | 2ull << 18 | 0ull << 20 | 2ull << 22 | 0ull << 24;
-    dx = (int)((PX >> (2 * f)) & 3) - 1;
-    dy = (int)((PY >> (2 * f)) & 3) - 1;
-    dz = (int)((PZ >> (2 * f)) & 3) - 1;
-}
 
 // ---- geometry tables, built once per (mode, N) and shared by every chain ----------------------
 // nbr[cell][L]: slot 0 = `cell` itself, then the ids of all other cells on the attack lines through it,
