@@ -122,7 +122,7 @@ struct SpecGeom<FULL, 0> {
     static __device__ __forceinline__ SLayout layout(const KArgs &a) { return a.sl; }
     static __device__ __forceinline__ int n(const KArgs &a) { return a.N; }
     static __device__ __forceinline__ int q(const KArgs &a) { return a.Q; }
-};   // 13*(N-1) <= 256 for every N the uint8 table admits
+};
 
 // ---- geometry tables, built once per (mode, N) and shared by every chain ----------------------
 // nbr[cell][L]: slot 0 = `cell` itself, then the ids of all other cells on the attack lines through it,
