@@ -348,9 +348,9 @@ static cudaError_t launch_g(const KArgs &a, bool replay, int grid, int block, si
     return replay ? launch_one<G, false, true>(a, grid, block, smem, s) : launch_one<G, false, false>(a, grid, block, smem, s);
 }
 
-template <bool FULL, bool REPLAY, bool EARLY, int NR, int LPC, int CN = 0>
+template <bool FULL, bool REPLAY, bool EARLY, int NR, int LPC, int CN = 0, int HK = -1>
 static cudaError_t launch_spec_one(const KArgs &a, int grid, int block, size_t smem, cudaStream_t s) {
-    auto k = spec_kernel<FULL, REPLAY, EARLY, NR, LPC, CN>;
+    auto k = spec_kernel<FULL, REPLAY, EARLY, NR, LPC, CN, HK>;
     // always the device maximum: the attribute is per function and per device, so concurrent host threads
     // (one engine each) must not race different values into it
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin);
@@ -364,6 +364,9 @@ static cudaError_t launch_spec_one(const KArgs &a, int grid, int block, size_t s
 template <bool FULL, int CN>
 static cudaError_t launch_spec_cn(const KArgs &a, int grid, int block, size_t smem, cudaStream_t s) {
     constexpr int NR = spec_layout(FULL, CN, CN * CN).rounds;
+    // ... and the history element kind with it (no history / uint16; int32 histories are a caller's choice at these sizes)
+    if (a.hist_kind == MCQ_HIST_NONE) return launch_spec_one<FULL, false, false, NR, 32, CN, 0>(a, grid, block, smem, s);
+    if (a.hist_kind == MCQ_HIST_U16) return launch_spec_one<FULL, false, false, NR, 32, CN, 1>(a, grid, block, smem, s);
     return launch_spec_one<FULL, false, false, NR, 32, CN>(a, grid, block, smem, s);
 }
 

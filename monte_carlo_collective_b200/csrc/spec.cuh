@@ -307,7 +307,7 @@ __device__ __forceinline__ float ex2_approx(float x) {
 // groups waste fewer evaluated proposals per round (at 3 % acceptance a 16-lane group commits
 // 12.9 of 16, a 32-lane group 20.7 of 32); committed moves are applied by the whole warp, one
 // chain after the other, so the table update keeps 32 lanes busy either way.
-template <bool FULL, bool REPLAY, bool EARLY, int NR, int LPC, int CN = 0>
+template <bool FULL, bool REPLAY, bool EARLY, int NR, int LPC, int CN = 0, int HK = -1>
 __global__ void __launch_bounds__(128, MCQ_SPEC_MINB) spec_kernel(const __grid_constant__ KArgs a) {
     constexpr unsigned FULLMASK = 0xffffffffu;
     constexpr int NF = FULL ? NFAM : NFAM - 1;
@@ -326,6 +326,7 @@ __global__ void __launch_bounds__(128, MCQ_SPEC_MINB) spec_kernel(const __grid_c
     const int N = SpecGeom<FULL, CN>::n(a), Q = SpecGeom<FULL, CN>::q(a);
     const SLayout sl = SpecGeom<FULL, CN>::layout(a);
     const int state_bytes = FULL ? 3 * Q : Q;
+    const int hist_kind = HK >= 0 ? HK : a.hist_kind;   // HK: history element kind compiled in (0 none, 1 uint16)
 
     // ---- CTA-shared geometry: shared-line bits at offset 0, cell -> wide id at sl.off_wide ----
     if (FULL) {
@@ -389,8 +390,8 @@ __global__ void __launch_bounds__(128, MCQ_SPEC_MINB) spec_kernel(const __grid_c
         if (a.t_begin == 0) {
             if (sub == 0) {
                 if (a.init_e) a.init_e[chain] = E;
-                if (a.hist_kind == 1) reinterpret_cast<uint16_t *>(a.hist)[(size_t)chain * a.hist_pitch] = (uint16_t)E;
-                else if (a.hist_kind == 2) reinterpret_cast<int *>(a.hist)[(size_t)chain * a.hist_pitch] = E;
+                if (hist_kind == 1) reinterpret_cast<uint16_t *>(a.hist)[(size_t)chain * a.hist_pitch] = (uint16_t)E;
+                else if (hist_kind == 2) reinterpret_cast<int *>(a.hist)[(size_t)chain * a.hist_pitch] = E;
             }
         } else {
             best = a.best_e[chain];
@@ -416,7 +417,7 @@ __global__ void __launch_bounds__(128, MCQ_SPEC_MINB) spec_kernel(const __grid_c
     [[maybe_unused]] uint32_t near = 0u;
     // history row, addressed by history index h = step + 1 (h_origin = index held by column 0)
     unsigned char *hrow = static_cast<unsigned char *>(a.hist) +
-                          ((long long)chain_c * a.hist_pitch - a.h_origin) * (a.hist_kind == 1 ? 2 : 4);
+                          ((long long)chain_c * a.hist_pitch - a.h_origin) * (hist_kind == 1 ? 2 : 4);
     uint32_t *abits_row = a.abits ? a.abits + (size_t)chain_c * a.abits_pitch : nullptr;
 
     while (CPW == 1 ? t < a.t_end : __any_sync(FULLMASK, t < a.t_end)) {
@@ -556,13 +557,13 @@ __global__ void __launch_bounds__(128, MCQ_SPEC_MINB) spec_kernel(const __grid_c
         }
         // history: steps t .. t+adv_h-1; all but an accepted last one keep the old energy
         // (two predicated stores rather than a branch)
-        {
+        if (HK != 0) {
             const bool wr = sub < adv_h;
             const int v = (sub == first) ? E_new : E;
             uint16_t *h16 = reinterpret_cast<uint16_t *>(ptr_mad(hrow + 2, (uint32_t)s, 2u));
             int *h32 = reinterpret_cast<int *>(ptr_mad(hrow + 4, (uint32_t)s, 4u));
-            if (wr && a.hist_kind == 1) *h16 = (uint16_t)v;
-            if (wr && a.hist_kind == 2) *h32 = v;
+            if (wr && hist_kind == 1) *h16 = (uint16_t)v;
+            if (HK < 0 && wr && hist_kind == 2) *h32 = v;
         }
         // ---------------- apply the committed moves: whole warp, one chain after the other ----------------
         const bool has = first >= 0;
