@@ -165,3 +165,8 @@ if which == "tablewide2":
     for n in (20, 21):
         for algo in ("table", "wide"):
             run("tablewide2", "board", n, 16384, 50000, algo=algo)
+
+if which == "wpc":
+    for w in (4, 2, 1):
+        run("wpc", "full_3d", 12, 20480, 200000, algo="table", warps_per_cta=w)
+        run("wpc", "board", 12, 20480, 100000, algo="table", warps_per_cta=w)

@@ -125,6 +125,20 @@ def test_cta_per_chain_kernel_on_large_boards(engine, mode, n):
         assert (h[groups == g].sum(axis=0) == st.stat_sum_e[g]).all()
 
 
+@pytest.mark.parametrize("n", [17, 19, 20])
+def test_table_and_cta_per_chain_kernels_agree_where_both_apply(engine, n):
+    """full_3d N = 19, 20 default to the CTA-per-chain kernel; the 16-bit conflict table still serves them on request."""
+    ns, nc = 1500, 12
+    betas = schedules.beta_table(LIN, ns)
+    seeds = np.arange(nc, dtype=np.uint64) + 77
+    runs = [engine.run("full_3d", n, ns, seeds, betas, history="full", accept_bits=True, algo=algo)
+            for algo in ("auto", "table", "wide", "lines")]
+    for r in runs[1:]:
+        for name in ("energy_history", "best_state", "final_state", "accept_bits", "steps_to_best"):
+            assert (getattr(r, name) == getattr(runs[0], name)).all(), name
+    _check_invariants(engine, "full_3d", n, runs[0])
+
+
 def test_initial_states(engine):
     from oracle import queens_numpy as qn
     for n in (5, 11, 12, 14):
