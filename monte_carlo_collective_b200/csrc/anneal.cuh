@@ -241,7 +241,7 @@ __device__ __forceinline__ int draw_digit(uint32_t &w, int n) {
 }
 
 template <int G, bool FULL, bool REPLAY>
-__global__ void __launch_bounds__(256) anneal_kernel(const __grid_constant__ KArgs a) {
+__global__ void __launch_bounds__(G == 1 ? 128 : 256, G == 1 ? 3 : 1) anneal_kernel(const __grid_constant__ KArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x;
     const int g = tid & (G - 1);

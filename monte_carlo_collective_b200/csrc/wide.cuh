@@ -11,7 +11,8 @@
 //   * the first accepted thread of the CTA is found with one ballot per warp and a minimum over the warps'
 //     candidates in shared memory; all steps before it were rejected and do not change the state, so the
 //     sequential chain of experiments.py:218-258 / :308-355 is reproduced exactly;
-//   * the winner's warp applies the move: lane f updates the two counters of family f, lane 0 the state;
+//   * the move is applied by two warps side by side: lane f of the winner's warp updates the two counters of
+//     family f, a lane of the next warp the state, the occupancy and the best-state journal;
 //   * two __syncthreads per round.  At the acceptance rates of a cold chain (~1 %) a round of 256 threads
 //     retires ~90 proposals;
 //   * the number of threads that evaluate (`width`, 32..256 in whole warps) follows the acceptance rate: a hot
@@ -29,7 +30,7 @@ namespace mcq {
 constexpr int WIDE_THREADS = 256;             // widest CTA (one per SM on the largest boards); 128 and 64 where more CTAs fit
 // (the ring of random words keeps 2 * blockDim steps)
 constexpr int WIDE_JCAP = 62;                 // journal of state elements changed since the last best-state snapshot
-constexpr int WIDE_XCH_BYTES = 256;           // exchange words (3 per warp), journal count, journal
+constexpr int WIDE_XCH_BYTES = 384;           // exchange words (3 per warp), journal count, journal, published moves (3 words per warp)
 
 template <bool FULL, bool EARLY, int NT>
 __global__ void __launch_bounds__(NT, 1) wide_kernel(const __grid_constant__ KArgs a) {
@@ -54,6 +55,7 @@ __global__ void __launch_bounds__(NT, 1) wide_kernel(const __grid_constant__ KAr
     const int st_bytes = a.lay.off_occ - a.lay.off_state;             // internal state bytes, rounded up to 4
     int *jcount = xch + 3 * NW;                                       // entries in the journal; > WIDE_JCAP: overflowed
     uint16_t *jrn = reinterpret_cast<uint16_t *>(xch + 3 * NW + 1);
+    uint32_t *xmv = reinterpret_cast<uint32_t *>(xch) + 64;           // [NW][3]: old cell, new cell, queen of each warp's first acceptance
 
     // ---- build the slab from the external state ----
     {
@@ -215,6 +217,13 @@ __global__ void __launch_bounds__(NT, 1) wide_kernel(const __grid_constant__ KAr
         const int wmin = __reduce_min_sync(FULLMASK, mine);
         int cmin = wmin;
         if constexpr (NT > 32) {
+            // each warp's first accepting thread publishes its move, so that after the barrier any warp can
+            // take part in applying the winner's (counters and state are updated by two warps side by side)
+            if (accept && mine == wmin) {
+                xmv[3 * warp] = (uint32_t)(i0 | (j0 << 8) | (k0c << 16));
+                xmv[3 * warp + 1] = (uint32_t)(i1 | (j1 << 8) | (k1c << 16));
+                xmv[3 * warp + 2] = (uint32_t)qsel;
+            }
             if (lane == 0) xch[warp] = wmin;
             __syncthreads();
             cmin = __reduce_min_sync(FULLMASK, lane < NW ? xch[lane] : NONE);
@@ -244,19 +253,30 @@ __global__ void __launch_bounds__(NT, 1) wide_kernel(const __grid_constant__ KAr
             if (a.hist_kind == 1) reinterpret_cast<uint16_t *>(hrow)[s + 1] = (uint16_t)v;
             else reinterpret_cast<int *>(hrow)[s + 1] = v;
         }
-        // ---------------- the winner's warp applies the move: lane f owns family f ----------------
-        if (has && warp == (first >> 5)) {
-            const int src = first & 31;
-            const uint32_t po = __shfl_sync(FULLMASK, (uint32_t)(i0 | (j0 << 8) | (k0c << 16)), src);
-            const uint32_t pn = __shfl_sync(FULLMASK, (uint32_t)(i1 | (j1 << 8) | (k1c << 16)), src);
-            const int wq = __shfl_sync(FULLMASK, qsel, src);
+        // ---------------- the move is applied: lane f of one warp owns family f, another warp the state ----------------
+        const int wf = first >> 5;                              // the winner's warp
+        const int ws = NT > 32 ? (wf + 1) & (NW - 1) : wf;      // the warp that updates state, occupancy and journal
+        if (has && (warp == wf || warp == ws)) {
+            uint32_t po, pn;
+            int wq;
+            if constexpr (NT > 32) {
+                po = xmv[3 * wf]; pn = xmv[3 * wf + 1]; wq = (int)xmv[3 * wf + 2];
+            } else {
+                const int src = first & 31;
+                po = __shfl_sync(FULLMASK, (uint32_t)(i0 | (j0 << 8) | (k0c << 16)), src);
+                pn = __shfl_sync(FULLMASK, (uint32_t)(i1 | (j1 << 8) | (k1c << 16)), src);
+                wq = __shfl_sync(FULLMASK, qsel, src);
+            }
             const int a0 = po & 255, b0 = (po >> 8) & 255, c0 = po >> 16, a1 = pn & 255, b1 = (pn >> 8) & 255, c1 = pn >> 16;
-            if (lane >= F0 && lane < NFAM) {
+            if (warp == wf && lane >= F0 && lane < NFAM) {
                 const int4 cf = a.coef[lane];
                 const int o = line_index(cf, a0, b0, c0), n = line_index(cf, a1, b1, c1);
-                if (o != n) { cnt[o] = (uint8_t)(cnt[o] - 1); cnt[n] = (uint8_t)(cnt[n] + 1); }
+                if (o != n) {
+                    const int vo = cnt[o], vn = cnt[n];
+                    cnt[o] = (uint8_t)(vo - 1); cnt[n] = (uint8_t)(vn + 1);
+                }
             }
-            if (lane == 31) {
+            if (warp == ws && lane == 31) {
                 const int jn = jfresh ? 0 : *jcount;
                 if (jn < WIDE_JCAP) jrn[jn] = (uint16_t)(FULL ? wq : a0 * N + b0);
                 *jcount = jn + 1;   // WIDE_JCAP + 1 and beyond: overflow, the next snapshot is a full copy
