@@ -8,6 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 OUT = os.path.join(PKG, "libmcq.so")
+PTXAS_LOG = os.path.join(PKG, "libmcq.ptxas.log")
 SOURCES = ["mcq_api.cu"]
 HEADERS = ["anneal.cuh", "spec.cuh", "wide.cuh", "philox.cuh", os.path.join("..", "..", "include", "mcq.h")]
 
@@ -28,11 +29,15 @@ def build(force=False, verbose=False):
     if not force and not needs_build():
         return OUT
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + SOURCES
+    # ptxas statistics are always collected: the log next to the library is what tests/test_host_logic.py reads to
+    # make sure no kernel spills (a silent change of ptxas' register choice once cost the thread-per-chain kernel 25 %)
+    cmd = [nvcc] + NVCC_FLAGS + ["-Xptxas", "-v", "-o", OUT] + SOURCES
     proc = subprocess.run(cmd, cwd=HERE, capture_output=True, text=True)
     if proc.returncode != 0:
         sys.stderr.write(proc.stdout + proc.stderr)
         raise RuntimeError("nvcc failed building libmcq.so")
+    with open(PTXAS_LOG, "w") as f:
+        f.write(proc.stderr)
     if verbose:
         sys.stderr.write(proc.stderr)
     return OUT

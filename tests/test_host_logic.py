@@ -164,3 +164,17 @@ def test_checkpoint_file_roundtrip(tmp_path):
     assert (c.mode, c.n, c.q, c.n_steps, c.n_chains, c.step) == (r.mode, 6, 36, 4096, 5, 1024)
     assert (c.record == r.record).all() and (c.final_state == r.final_state).all() and (c.best_state == r.best_state).all()
     assert c.record.dtype == np.int32 and c.final_state.dtype == np.uint8
+
+
+def test_no_kernel_spills_registers():
+    """ptxas statistics of the build: every kernel fits its register budget without spilling."""
+    import re
+    import __graft_entry__ as ge
+    ge.build()
+    from monte_carlo_collective_b200.csrc import build as b
+    if not os.path.isfile(b.PTXAS_LOG):
+        b.build(force=True)
+    txt = open(b.PTXAS_LOG).read()
+    spills = [(int(a), int(c)) for a, c in re.findall(r"(\d+) bytes spill stores, (\d+) bytes spill loads", txt)]
+    assert len(spills) > 100                      # every instantiation is listed
+    assert all(s == (0, 0) for s in spills), [s for s in spills if s != (0, 0)]
