@@ -230,11 +230,8 @@ def main():
     dev = torch.device(f"cuda:{local}")
 
     # ---- synthetic inputs ----
-    betas = np.stack([schedules.beta_table(p, ns) for p in SCHEDULES])
-    tab_h = schedules.to_device_table(betas)                       # [5, ns] float32
     seeds_h = chain_seeds(rank, reps)
     groups_h = np.repeat(np.arange(ng, dtype=np.int32), reps)
-    tab_d = torch.from_numpy(tab_h).to(dev)
     seeds_d = torch.from_numpy(seeds_h.view(np.int64)).to(dev)
     groups_d = torch.from_numpy(groups_h).to(dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -242,7 +239,7 @@ def main():
     out_d = {}
 
     def device_pass():
-        r = eng.run("full_3d", N_BOARD, ns, seeds_d, None, groups=groups_d, beta_device_table=tab_d, history="stats",
+        r = eng.run("full_3d", N_BOARD, ns, seeds_d, schedules=SCHEDULES, groups=groups_d, history="stats",
                     n_bins=100, device_buffers=True, lanes_per_chain=args.lanes, stream=stream.cuda_stream, out=out_d)
         for k in ("stat_sum_e", "stat_sum_e2", "best_energy", "final_energy", "steps_to_best", "n_accepted",
                   "steps_done", "initial_energy", "final_state", "best_state", "accept_hist"):
@@ -297,12 +294,12 @@ def main():
     e2e = None
     if not args.no_e2e:
         out_h = {}
-        h2d = seeds_h.nbytes + groups_h.nbytes + tab_h.nbytes
+        h2d = seeds_h.nbytes + groups_h.nbytes + 32 * ng   # seeds, group ids, five schedule parameter records
         times = []
         for it in range(min(args.warmup, 1) + args.steps):
             sync_all()
             t0 = time.perf_counter()
-            rh = eng.run("full_3d", N_BOARD, ns, seeds_h, None, groups=groups_h, beta_device_table=tab_h,
+            rh = eng.run("full_3d", N_BOARD, ns, seeds_h, schedules=SCHEDULES, groups=groups_h,
                          history="stats", n_bins=100, lanes_per_chain=args.lanes, out=out_h)
             sync_all()
             dt = time.perf_counter() - t0

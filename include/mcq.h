@@ -16,6 +16,10 @@
  *                          experiments.py:199-279, :282-376, :475-573
  *   mcq_philox4x32_10   -- the counter-based generator the chains draw from (host copy,
  *                          for known-answer tests; the reference uses NumPy's MT19937)
+ *   mcq_philox4x32_10_device -- the same generator as compiled for the GPU (known-answer tests
+ *                          of the device code itself)
+ *   mcq_beta_table      <- constant_beta / linear / exponential / logarithmic / sinusoidal
+ *                          annealing schedules, experiments.py:13-77, evaluated on the device
  *
  * Conventions: plain C types only; the caller owns every buffer (host or device, see
  * `mem`); nothing returned is owned by the library except the opaque context.  Every
@@ -33,7 +37,7 @@
 extern "C" {
 #endif
 
-#define MCQ_ABI_VERSION 2
+#define MCQ_ABI_VERSION 3
 #define MCQ_RECORD_INTS 8
 
 /* state space (experiments.py:497-502: "board" or anything else => full_3d) */
@@ -62,6 +66,21 @@ extern "C" {
 #define MCQ_ALGO_TABLE 2  /* per-cell conflict table, one warp per chain, speculative rounds (spec.cuh) */
 #define MCQ_ALGO_GMEM 3   /* line counters in global memory, one thread per chain: boards too large for shared memory */
 #define MCQ_ALGO_WIDE 4   /* line counters in shared memory, one CTA per chain, speculative rounds of 256 steps (wide.cuh) */
+
+/* inverse-temperature schedules (experiments.py:13-77), evaluated on the device in float64 */
+#define MCQ_SCHED_CONSTANT 0    /* beta_const */
+#define MCQ_SCHED_LINEAR 1      /* b0 + (s/(n-1)) (b1-b0); b1 if n <= 1 */
+#define MCQ_SCHED_EXPONENTIAL 2 /* b0 exp(ln(b1/b0) s/(n-1)) */
+#define MCQ_SCHED_LOGARITHMIC 3 /* b0 + (b1-b0) ln(1+s)/ln(1+n) */
+#define MCQ_SCHED_SINUSOIDAL 4  /* b0 + (b1-b0)(1-cos(pi s/n))/2 */
+
+typedef struct mcq_schedule {
+    int32_t type; /* MCQ_SCHED_* */
+    int32_t reserved;
+    double beta_const;
+    double beta_start;
+    double beta_end;
+} mcq_schedule;
 
 /* error codes */
 #define MCQ_OK 0
@@ -92,10 +111,12 @@ typedef struct mcq_run_params {
     /* ---- inputs ---- */
     const uint64_t *chain_seeds; /* [n_chains] Philox key; depends on the chain only, never on placement */
     const int32_t *chain_group;  /* [n_chains] in [0,n_groups), or NULL = all 0 */
-    const float *beta_log2e;     /* [n_groups][n_steps] float32, -beta_t*log2(e); production path */
+    const mcq_schedule *schedules; /* [n_groups] schedule parameters: beta_t is evaluated on the device (production path;
+                                      HOST memory always), or NULL when beta_f64 carries a tabulated schedule */
     const uint8_t *init_states;  /* [n_chains][state_bytes] when init_mode == EXPLICIT, else NULL */
 
-    /* ---- replay of a recorded proposal / uniform stream (all three or none) ---- */
+    /* beta_f64 alone: production run on a schedule tabulated by the caller (an arbitrary closure of step).
+       ---- replay of a recorded proposal / uniform stream: beta_f64, replay_moves and replay_uniforms ---- */
     const double *beta_f64;         /* [n_groups][n_steps] exact float64 betas */
     const uint32_t *replay_moves;   /* [n_chains][n_steps]; board: i | j<<8 | k'<<16;
                                        full_3d: q | i<<12 | j<<18 | k<<24 */
@@ -110,6 +131,8 @@ typedef struct mcq_run_params {
        experiments.py:591-595): sums over the chains of the group of E and E^2 */
     int64_t *stat_sum_e;   /* [n_groups][n_steps+1] or NULL */
     int64_t *stat_sum_e2;  /* [n_groups][n_steps+1] or NULL (both or none) */
+    int32_t *stat_count;   /* [n_groups][n_steps+1] or NULL: chains of the group that have an energy at that index
+                              (all of them unless the board patience stopped some: the denominator of the mean) */
     /* accepted moves per step bin (plot_acceptance_rates_binned, experiments.py:660-686) */
     int32_t n_bins;            /* 0 = none */
     const int32_t *bin_starts; /* [n_bins+1] first step of each bin; bin_starts[n_bins] = n_steps (HOST memory always) */
@@ -124,7 +147,9 @@ typedef struct mcq_run_params {
     int32_t *steps_done;     /* [n_chains] history length - 1 (== n_steps unless early-stopped) */
     uint8_t *final_state;    /* [n_chains][state_bytes] */
     uint8_t *best_state;     /* [n_chains][state_bytes] state at the first visit of best_energy */
-    uint32_t *n_near_threshold; /* [n_chains] replay only: accept decisions with |u - exp(-beta dE)| < 1e-6 */
+    uint32_t *n_near_threshold; /* [n_chains] replay: accept decisions with |u - exp(-beta dE)| < 1e-6; production:
+                                   decisions inside the float32 error band, taken with the float64 rule instead */
+    uint32_t *n_fp32_flips;     /* [n_chains] production: band decisions float32 alone would have got wrong */
 
     /* ---- measurements ---- */
     float *kernel_ms;       /* HOST pointer: sum of annealing-kernel durations (CUDA events) */
@@ -137,6 +162,8 @@ typedef struct mcq_run_params {
     int32_t max_chains_per_sm;
     int32_t algo;            /* MCQ_ALGO_*; a non-zero lanes_per_chain with AUTO selects LINES */
     void *stream;            /* cudaStream_t, or NULL for the context's own stream */
+    int32_t accept_all_f64;  /* non-zero: every uphill accept decision is taken with the float64 rule (the band is
+                                infinite); same chains, slower -- a test of the float32 fast path */
 
     /* ---- checkpoint / resume (the reference has none: SURVEY 5.4; chains are resumable here because the random
      *      stream is counter-based -- step s of a chain depends on (seed, s) only) ----
@@ -193,6 +220,12 @@ int mcq_host_free(void *ptr);
 
 /* Philox4x32-10 (Salmon et al., SC'11), host implementation identical to the device one */
 void mcq_philox4x32_10(const uint32_t counter[4], const uint32_t key[2], uint32_t out[4]);
+/* the device build of the same function: n calls, counters [n][4], keys [n][2], out [n][4] (HOST pointers) */
+int mcq_philox4x32_10_device(mcq_ctx *ctx, int n, const uint32_t *counters, const uint32_t *keys, uint32_t *out);
+
+/* beta(step) of `n_groups` schedules evaluated on the device: out_beta[g][s] float64 (the value the float64 accept
+ * rule uses), out_c[g][s] float32(-beta log2 e) (what the float32 fast path reads); either may be NULL.  HOST pointers. */
+int mcq_beta_table(mcq_ctx *ctx, int n_groups, const mcq_schedule *schedules, int n_steps, double *out_beta, float *out_c);
 
 #ifdef __cplusplus
 }

@@ -17,8 +17,9 @@ INIT_RANDOM, INIT_LATIN, INIT_KLARNER, INIT_EXPLICIT = 0, 1, 2, 3
 MEM_HOST, MEM_DEVICE = 0, 1
 HIST_NONE, HIST_U16, HIST_I32 = 0, 1, 2
 OK, EINVAL, ECUDA, ENOMEM, EREPLAY = 0, -1, -2, -3, -4
-ABI_VERSION = 2
-ALGO_AUTO, ALGO_LINES, ALGO_TABLE, ALGO_GMEM = 0, 1, 2, 3
+ABI_VERSION = 3
+ALGO_AUTO, ALGO_LINES, ALGO_TABLE, ALGO_GMEM, ALGO_WIDE = 0, 1, 2, 3, 4
+SCHED_CONSTANT, SCHED_LINEAR, SCHED_EXPONENTIAL, SCHED_LOGARITHMIC, SCHED_SINUSOIDAL = 0, 1, 2, 3, 4
 
 
 class McqError(RuntimeError):
@@ -27,6 +28,12 @@ class McqError(RuntimeError):
     def __init__(self, code, message):
         super().__init__(f"libmcq error {code}: {message}")
         self.code = code
+
+
+class Schedule(C.Structure):
+    """Mirror of ``mcq_schedule``: one inverse-temperature law (experiments.py:13-77)."""
+    _fields_ = [("type", C.c_int32), ("reserved", C.c_int32), ("beta_const", C.c_double), ("beta_start", C.c_double),
+                ("beta_end", C.c_double)]
 
 
 class RunParams(C.Structure):
@@ -44,7 +51,7 @@ class RunParams(C.Structure):
         ("early_stop_patience", C.c_int32),
         ("chain_seeds", C.c_void_p),
         ("chain_group", C.c_void_p),
-        ("beta_log2e", C.c_void_p),
+        ("schedules", C.c_void_p),
         ("init_states", C.c_void_p),
         ("beta_f64", C.c_void_p),
         ("replay_moves", C.c_void_p),
@@ -55,6 +62,7 @@ class RunParams(C.Structure):
         ("accept_bits", C.c_void_p),
         ("stat_sum_e", C.c_void_p),
         ("stat_sum_e2", C.c_void_p),
+        ("stat_count", C.c_void_p),
         ("n_bins", C.c_int32),
         ("bin_starts", C.c_void_p),
         ("accept_hist", C.c_void_p),
@@ -67,6 +75,7 @@ class RunParams(C.Structure):
         ("final_state", C.c_void_p),
         ("best_state", C.c_void_p),
         ("n_near_threshold", C.c_void_p),
+        ("n_fp32_flips", C.c_void_p),
         ("kernel_ms", C.c_void_p),
         ("gpu_launches", C.c_void_p),
         ("lanes_per_chain", C.c_int32),
@@ -75,6 +84,7 @@ class RunParams(C.Structure):
         ("max_chains_per_sm", C.c_int32),
         ("algo", C.c_int32),
         ("stream", C.c_void_p),
+        ("accept_all_f64", C.c_int32),
         ("start_step", C.c_int32),
         ("stop_step", C.c_int32),
         ("resume_record", C.c_void_p),
@@ -103,6 +113,8 @@ SYMBOLS = [
     ("mcq_host_alloc", C.c_int, [C.POINTER(C.c_void_p), C.c_uint64]),
     ("mcq_host_free", C.c_int, [C.c_void_p]),
     ("mcq_philox4x32_10", None, [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
+    ("mcq_philox4x32_10_device", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("mcq_beta_table", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
 ]
 
 _lib = None

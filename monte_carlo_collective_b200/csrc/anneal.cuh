@@ -25,6 +25,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "accept.cuh"
 #include "philox.cuh"
 
 namespace mcq {
@@ -78,9 +79,18 @@ struct KArgs {
     // per-chain inputs
     const unsigned long long *seeds;
     const int *group;     // may be null
-    const float *beta_c;  // [n_groups][n_steps]  -beta*log2(e)
+    const float *beta_c;  // [n_groups][n_steps]  float32(-beta*log2(e)), built on the device (beta_table_kernel)
+    const SchedDev *sched; // [n_groups] schedule parameters (float64 rule of the accept test), or
+    float band_abs;        // absolute part of the float32 error band (4; +inf = every uphill decision in float64)
+    uint32_t *flip_cnt;    // [n_chains] production: band decisions that float32 alone would have got wrong
+    // cross-replica statistics in difference form: column h of group g receives what the chains of g add to
+    // sum E, sum E^2 and the number of live chains when they reach history index h (mcq_run integrates them)
+    unsigned long long *dsum_e, *dsum_e2;
+    int *dcount;           // may be null
+    long long stat_pitch;  // elements per group row (n_steps + 1)
+    int stat_rows32;       // n_groups * stat_pitch < 2^31: kernels may index the rows with 32 bits
     // replay
-    const double *beta64;
+    const double *beta64;  // replay: exact betas; production: float64 table of a tabulated closure (else `sched`)
     const uint32_t *rmoves;
     const double *runif;
     uint32_t *near_cnt;
@@ -112,6 +122,18 @@ struct KArgs {
 
 __device__ __forceinline__ int line_index(const int4 c, int i, int j, int k) {
     return c.x * i + c.y * j + c.z * k + c.w;
+}
+
+// statistics in difference form (see KArgs::dsum_e): one lane per chain calls this when the chain's energy
+// changes from e_old to e_new at history index h (dc = change of the live-chain count)
+__device__ __forceinline__ void stat_delta(const KArgs &a, int grp, long long h, int e_old, int e_new, int dc) {
+    const size_t idx = (size_t)grp * (size_t)a.stat_pitch + (size_t)h;
+    const long long de = (long long)e_new - (long long)e_old;
+    if (de) {
+        atomicAdd(a.dsum_e + idx, (unsigned long long)de);
+        atomicAdd(a.dsum_e2 + idx, (unsigned long long)(de * ((long long)e_new + (long long)e_old)));
+    }
+    if (dc && a.dcount) atomicAdd(a.dcount + idx, dc);
 }
 
 template <int G>
@@ -279,6 +301,7 @@ __global__ void __launch_bounds__(G == 1 ? 128 : 256, G == 1 ? 3 : 1) anneal_ker
             if (a.init_e) a.init_e[chain] = E;
             if (a.hist_kind == 1) reinterpret_cast<uint16_t *>(a.hist)[(size_t)chain * a.hist_pitch] = (uint16_t)E;
             else if (a.hist_kind == 2) reinterpret_cast<int *>(a.hist)[(size_t)chain * a.hist_pitch] = E;
+            if (a.dsum_e) stat_delta(a, a.group ? a.group[chain] : 0, 0, 0, E, 1);
         }
     } else if (live) {
         best = a.best_e[chain];
@@ -308,7 +331,7 @@ __global__ void __launch_bounds__(G == 1 ? 128 : 256, G == 1 ? 3 : 1) anneal_ker
     int bin = a.bin_at_begin;
     int next_edge = a.n_bins > 0 ? a.bin_starts[bin + 1] : 0x7fffffff;
     uint32_t accbits = 0u;
-    uint32_t near = 0u;
+    uint32_t near = 0u, flips = 0u;
     int blk_t0 = a.t_begin;  // first step staged in the current history block
 
     for (int t = a.t_begin; t < a.t_end; ++t) {
@@ -323,7 +346,7 @@ __global__ void __launch_bounds__(G == 1 ? 128 : 256, G == 1 ? 3 : 1) anneal_ker
                 w1 = make_uint4(mv_row[ts], (uint32_t)__double2loint(u), (uint32_t)__double2hiint(u), (uint32_t)__double2loint(b));
                 w1_4 = (uint32_t)__double2hiint(b);
             } else {
-                const Philox4 r = philox4x32_10((uint32_t)ts, 0u, 0u, PHILOX_DOMAIN_STEP, k0, k1);
+                const Philox4 r = chain_words((uint32_t)ts, k0, k1, PHILOX_STREAM_STEP);
                 w1 = make_uint4(r.x, r.y, r.z, r.w);
                 w1_4 = __float_as_uint(c_pref);                       // fetched one step ahead
                 if (live && ts + 1 < a.t_end) c_pref = __ldg(beta_row + ts + 1);
@@ -340,7 +363,7 @@ __global__ void __launch_bounds__(G == 1 ? 128 : 256, G == 1 ? 3 : 1) anneal_ker
                         p[1] = (uint32_t)__double2loint(u); p[2] = (uint32_t)__double2hiint(u);
                         p[3] = (uint32_t)__double2loint(b); p[4] = (uint32_t)__double2hiint(b);
                     } else {
-                        const Philox4 r = philox4x32_10((uint32_t)ts, 0u, 0u, PHILOX_DOMAIN_STEP, k0, k1);
+                        const Philox4 r = chain_words((uint32_t)ts, k0, k1, PHILOX_STREAM_STEP);
                         *reinterpret_cast<uint4 *>(p) = make_uint4(r.x, r.y, r.z, r.w);
                         p[4] = __float_as_uint(c_pref);
                         const int tn = ts + PB;
@@ -385,7 +408,7 @@ __global__ void __launch_bounds__(G == 1 ? 128 : 256, G == 1 ? 3 : 1) anneal_ker
                     else if (tries == 1) word = w.x * (uint32_t)a.Q;   // what the queen draw left of word x
                     else {
                         const int e = tries - 2;
-                        const Philox4 r = philox4x32_10((uint32_t)t, 0u, 1u + (uint32_t)(e >> 2), PHILOX_DOMAIN_STEP, k0, k1);
+                        const Philox4 r = chain_words((uint32_t)t, k0, k1, 1u + (uint32_t)(e >> 2));
                         const int s = e & 3;
                         word = s == 0 ? r.x : s == 1 ? r.y : s == 2 ? r.z : r.w;
                     }
@@ -425,9 +448,14 @@ __global__ void __launch_bounds__(G == 1 ? 128 : 256, G == 1 ? 3 : 1) anneal_ker
             if (active && !bad && fabs(u - p) < 1e-6) ++near;
             if (bad) { accept = false; if (active && g == 0) atomicAdd(a.replay_err, 1u); }
         } else {
-            const float p = exp2f(__uint_as_float(w4) * (float)dE);   // exp(-beta*dE)
-            const uint32_t thr = __float2uint_rz(p * 4294967296.0f);  // saturates at 2^32-1
-            accept = (dE <= 0) || (w.z < thr);
+            bool near_band;
+            metropolis_fast(dE, __uint_as_float(w4), w.z, a.band_abs, accept, near_band);
+            if (near_band && active) {   // inside the float32 error band: the float64 rule decides (accept.cuh)
+                const bool exact = metropolis_exact_call(a.sched, a.beta64, a.n_steps, grp, k0, k1, t, dE, w.z);
+                ++near;
+                flips += (uint32_t)(exact != accept);
+                accept = exact;
+            }
         }
         accept = accept && active;
 
@@ -444,6 +472,7 @@ __global__ void __launch_bounds__(G == 1 ? 128 : 256, G == 1 ? 3 : 1) anneal_ker
                     st[i0 * N + j0] = (unsigned char)k1c;
                 }
             }
+            if (a.dsum_e && g == 0 && dE != 0) stat_delta(a, grp, (long long)t + 1, E, E + dE, 0);
             E += dE;
             ++n_acc;
             accbits |= 1u << (t & 31);
@@ -502,6 +531,7 @@ __global__ void __launch_bounds__(G == 1 ? 128 : 256, G == 1 ? 3 : 1) anneal_ker
         if (stop_now) {
             active = false;
             done = t;
+            if (a.dsum_e && g == 0) stat_delta(a, grp, (long long)t + 1, E, 0, -1);   // no energy is appended from here on
             if (g == 0 && a.acc_hist) a.acc_hist[(size_t)chain * a.n_bins + bin] = (uint32_t)(n_acc - bin_mark);
         }
         if (active && g == 0 && (a.hist_kind || G > 1)) hst[t & (HBLK - 1)] = E;
@@ -551,7 +581,8 @@ __global__ void __launch_bounds__(G == 1 ? 128 : 256, G == 1 ? 3 : 1) anneal_ker
             a.stale[chain] = stale;
             a.bin_mark[chain] = bin_mark;
             a.steps_done[chain] = done;
-            if (REPLAY && a.near_cnt) a.near_cnt[chain] += near;
+            if (a.near_cnt) a.near_cnt[chain] += near;
+            if (!REPLAY && a.flip_cnt) a.flip_cnt[chain] += flips;
         }
     }
 }

@@ -126,7 +126,7 @@ __global__ void init_states_kernel(int full, int N, int Q, int init_mode, int n_
     Philox4 r;
     int have = 0;
     auto next_word = [&]() -> uint32_t {
-        if (have == 0) { r = philox4x32_10(ctr++, 0u, 0u, PHILOX_DOMAIN_INIT, k0, k1); have = 4; }
+        if (have == 0) { r = chain_words(ctr++, k0, k1, PHILOX_STREAM_INIT); have = 4; }
         const uint32_t v = have == 4 ? r.x : have == 3 ? r.y : have == 2 ? r.z : r.w;
         --have;
         return v;
@@ -239,58 +239,73 @@ __global__ void __launch_bounds__(32) delta_kernel(const __grid_constant__ KArgs
     }
 }
 
-// Column sums of a [chain][step] history tile: per group, sum E and sum E^2 (experiments.py:593-595).
-// grid.x tiles the columns, grid.y slices the chains; partial sums go out with 64-bit atomics.
-// VEC consecutive columns per thread (16-byte loads when the tile is aligned), 4 chains in flight.
-template <typename T, int VEC>
-__global__ void __launch_bounds__(128) stats_kernel(const T *hist, long long pitch, int n_cols, long long h_origin, int n_chains,
-                                                    const int *group, const int *steps_done, unsigned long long *sum_e,
-                                                    unsigned long long *sum_e2, long long stat_pitch) {
-    const int col = (blockIdx.x * blockDim.x + threadIdx.x) * VEC;
-    if (col >= n_cols) return;
-    const int nv = min(VEC, n_cols - col);      // valid columns of this thread (tail of the tile)
-    const long long h = h_origin + col;
-    const int per = (n_chains + gridDim.y - 1) / gridDim.y;
-    const int c0 = blockIdx.y * per, c1 = min(n_chains, c0 + per);
-    unsigned long long s[VEC], s2[VEC];
+// Cross-replica statistics (experiments.py:593-595: mean and std of the energy over the runs, per step).  The chain
+// kernels deposit DIFFERENCES: column h of a group's row receives what its chains add to sum E / sum E^2 / the
+// live-chain count when they reach history index h (an accepted move, the initial energy at h = 0, an early
+// stop).  This kernel integrates columns [h0, h1] of every row in place, with the value of column h0-1 as the
+// carry (0 when h0 == 0), so that the rows hold the sums themselves.  One CTA per row, tiles of 4096 columns.
+template <typename T>
+__global__ void __launch_bounds__(1024) stat_integrate_kernel(T *rows, long long pitch, long long h0, long long h1) {
+    __shared__ T warp_tot[32];
+    __shared__ T carry_s;
+    T *row = rows + (size_t)blockIdx.x * pitch;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) carry_s = h0 > 0 ? row[h0 - 1] : (T)0;
+    __syncthreads();
+    for (long long base = h0; base <= h1; base += 4096) {
+        T v[4];
+        T run = 0;
 #pragma unroll
-    for (int v = 0; v < VEC; ++v) { s[v] = 0; s2[v] = 0; }
-    auto flush = [&](int g) {
-#pragma unroll
-        for (int v = 0; v < VEC; ++v)
-            if (v < nv && (s[v] | s2[v])) {
-                atomicAdd(&sum_e[(size_t)g * stat_pitch + h + v], s[v]);
-                atomicAdd(&sum_e2[(size_t)g * stat_pitch + h + v], s2[v]);
-                s[v] = 0; s2[v] = 0;
-            }
-    };
-    struct alignas(sizeof(T) * VEC) Pack { T e[VEC]; };
-    int cur = c0 < c1 ? (group ? group[c0] : 0) : 0;
-    constexpr int U = 4;
-    for (int c = c0; c < c1; c += U) {
-        Pack p[U];
-        int gr[U], sd[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int cc = min(c + u, c1 - 1);
-            if (VEC > 1) p[u] = *reinterpret_cast<const Pack *>(hist + (size_t)cc * pitch + col);
-            else p[u].e[0] = hist[(size_t)cc * pitch + col];
-            gr[u] = group ? group[cc] : 0;
-            sd[u] = steps_done[cc];
+        for (int e = 0; e < 4; ++e) {
+            const long long h = base + 4 * tid + e;
+            v[e] = h <= h1 ? row[h] : (T)0;
+            run += v[e];
+            v[e] = run;
         }
+        T inc = run;   // inclusive scan of the threads' totals: warp, then across warps
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            if (c + u >= c1) break;
-            if (gr[u] != cur) { flush(cur); cur = gr[u]; }
-#pragma unroll
-            for (int v = 0; v < VEC; ++v) {
-                // an early-stopped chain has no energy appended beyond its last step
-                const unsigned long long x = (h + v <= sd[u]) ? (unsigned long long)p[u].e[v] : 0ull;
-                s[v] += x; s2[v] += x * x;
-            }
+        for (int d = 1; d < 32; d <<= 1) {
+            const T o = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += o;
         }
+        if (lane == 31) warp_tot[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            T w = warp_tot[lane];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const T o = __shfl_up_sync(0xffffffffu, w, d);
+                if (lane >= d) w += o;
+            }
+            warp_tot[lane] = w;
+        }
+        __syncthreads();
+        const T before = carry_s + (warp > 0 ? warp_tot[warp - 1] : (T)0) + (inc - run);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const long long h = base + 4 * tid + e;
+            if (h <= h1) row[h] = before + v[e];
+        }
+        __syncthreads();
+        if (tid == 1023) carry_s = before + run;
+        __syncthreads();
     }
-    flush(cur);
+}
+
+// device build of the generator, for known-answer tests of the compiled device code
+__global__ void philox_kat_kernel(int n, const uint32_t *ctr, const uint32_t *key, uint32_t *out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Philox4 r = philox4x32_10(ctr[4 * i], ctr[4 * i + 1], ctr[4 * i + 2], ctr[4 * i + 3], key[2 * i], key[2 * i + 1]);
+    out[4 * i] = r.x; out[4 * i + 1] = r.y; out[4 * i + 2] = r.z; out[4 * i + 3] = r.w;
+}
+
+// float64 beta(step) of parametrised schedules (what metropolis_exact evaluates on demand)
+__global__ void beta64_table_kernel(const SchedDev *sched, int n_groups, int n_steps, double *out) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)n_groups * n_steps) return;
+    const int g = (int)(idx / n_steps);
+    out[idx] = sched_beta64(sched[g], n_steps, (int)(idx - (long long)g * n_steps));
 }
 
 // ------------------------------------------------------------------------------------------
@@ -311,9 +326,20 @@ struct DevBuf {
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
+// events of one call, destroyed on every return path
+struct EventBag {
+    std::vector<cudaEvent_t> ev;
+    cudaError_t make(cudaEvent_t *out, unsigned flags) {
+        cudaError_t e = cudaEventCreateWithFlags(out, flags);
+        if (e == cudaSuccess) ev.push_back(*out);
+        return e;
+    }
+    ~EventBag() { for (cudaEvent_t e : ev) cudaEventDestroy(e); }
+};
+
 enum BufId {
     B_SEEDS, B_GROUP, B_BETA, B_INIT, B_RMOVES, B_RUNIF, B_STATE, B_BEST, B_REC, B_OCC, B_HIST0, B_HIST1,
-    B_ABITS, B_ACCH, B_BINS, B_STATE_IN, B_MOVES, B_OUT, B_SUME, B_SUME2, B_GSLAB, B_NBUF
+    B_ABITS, B_ACCH, B_BINS, B_STATE_IN, B_MOVES, B_OUT, B_SUME, B_SUME2, B_SCNT, B_GSLAB, B_SCHED, B_BETA64, B_NBUF
 };
 
 }  // namespace mcq
@@ -364,16 +390,21 @@ static cudaError_t launch_spec_one(const KArgs &a, int grid, int block, size_t s
 template <bool FULL, int CN>
 static cudaError_t launch_spec_cn(const KArgs &a, int grid, int block, size_t smem, cudaStream_t s) {
     constexpr int NR = spec_layout(FULL, CN, CN * CN).rounds;
-    // ... and the history element kind with it (no history / uint16; int32 histories are a caller's choice at these sizes)
-    if (a.hist_kind == MCQ_HIST_NONE) return launch_spec_one<FULL, false, false, NR, 32, CN, 0>(a, grid, block, smem, s);
+    // ... and the per-step output with it: nothing, the statistics in difference form, or a uint16 history
+    // (callers check fixed_n_serves() first: other combinations run the kernels that take the geometry at run time)
     if (a.hist_kind == MCQ_HIST_U16) return launch_spec_one<FULL, false, false, NR, 32, CN, 1>(a, grid, block, smem, s);
-    return launch_spec_one<FULL, false, false, NR, 32, CN>(a, grid, block, smem, s);
+    if (a.dsum_e) return launch_spec_one<FULL, false, false, NR, 32, CN, 3>(a, grid, block, smem, s);   // (row offsets are 32-bit there)
+    return launch_spec_one<FULL, false, false, NR, 32, CN, 0>(a, grid, block, smem, s);
+}
+static inline bool fixed_n_serves(const KArgs &a) {
+    if (a.dsum_e && !a.stat_rows32) return false;
+    return a.hist_kind == MCQ_HIST_NONE || (a.hist_kind == MCQ_HIST_U16 && !a.dsum_e);
 }
 
 // production kernels have the neighbour-row length compiled in; replay / early-stop ones take it at run time
 template <bool FULL, int LPC>
 static cudaError_t launch_spec_nr(const KArgs &a, int grid, int block, size_t smem, cudaStream_t s) {
-    if (LPC == 32 && a.Q == a.N * a.N && !getenv("MCQ_NO_FIXED_N")) {
+    if (LPC == 32 && a.Q == a.N * a.N && fixed_n_serves(a) && !getenv("MCQ_NO_FIXED_N")) {
         switch (a.N) {
             case 8: return launch_spec_cn<FULL, 8>(a, grid, block, smem, s);
             case 9: return launch_spec_cn<FULL, 9>(a, grid, block, smem, s);
@@ -580,6 +611,50 @@ void mcq_philox4x32_10(const uint32_t counter[4], const uint32_t key[2], uint32_
     out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
 }
 
+int mcq_philox4x32_10_device(mcq_ctx *ctx, int n, const uint32_t *counters, const uint32_t *keys, uint32_t *out) {
+    if (!ctx || n < 0 || (n && (!counters || !keys || !out))) return fail(MCQ_EINVAL, "bad arguments");
+    if (n == 0) return 0;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    if (ctx->buf[B_MOVES].ensure((size_t)n * 16) || ctx->buf[B_OUT].ensure((size_t)n * 16) || ctx->buf[B_SEEDS].ensure((size_t)n * 8))
+        return fail(MCQ_ENOMEM, "device allocation failed");
+    CUDA_TRY(cudaMemcpyAsync(ctx->buf[B_MOVES].p, counters, (size_t)n * 16, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(ctx->buf[B_SEEDS].p, keys, (size_t)n * 8, cudaMemcpyHostToDevice, s));
+    philox_kat_kernel<<<(n + 127) / 128, 128, 0, s>>>(n, static_cast<const uint32_t *>(ctx->buf[B_MOVES].p),
+                                                      static_cast<const uint32_t *>(ctx->buf[B_SEEDS].p), static_cast<uint32_t *>(ctx->buf[B_OUT].p));
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(out, ctx->buf[B_OUT].p, (size_t)n * 16, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return 0;
+}
+
+int mcq_beta_table(mcq_ctx *ctx, int n_groups, const mcq_schedule *schedules, int n_steps, double *out_beta, float *out_c) {
+    if (!ctx || n_groups < 1 || n_steps < 0 || !schedules) return fail(MCQ_EINVAL, "bad arguments");
+    for (int g = 0; g < n_groups; ++g)
+        if (schedules[g].type < MCQ_SCHED_CONSTANT || schedules[g].type > MCQ_SCHED_SINUSOIDAL) return fail(MCQ_EINVAL, "unknown schedule type");
+    if (n_steps == 0) return 0;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    const long long cells = (long long)n_groups * n_steps;
+    if (ctx->buf[B_SCHED].ensure((size_t)n_groups * sizeof(SchedDev)) || ctx->buf[B_BETA64].ensure((size_t)cells * 8) ||
+        ctx->buf[B_BETA].ensure((size_t)cells * 4)) return fail(MCQ_ENOMEM, "device allocation failed");
+    CUDA_TRY(cudaMemcpyAsync(ctx->buf[B_SCHED].p, schedules, (size_t)n_groups * sizeof(SchedDev), cudaMemcpyHostToDevice, s));
+    const SchedDev *sd = static_cast<const SchedDev *>(ctx->buf[B_SCHED].p);
+    const unsigned grid = (unsigned)((cells + 255) / 256);
+    if (out_beta) {
+        beta64_table_kernel<<<grid, 256, 0, s>>>(sd, n_groups, n_steps, static_cast<double *>(ctx->buf[B_BETA64].p));
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaMemcpyAsync(out_beta, ctx->buf[B_BETA64].p, (size_t)cells * 8, cudaMemcpyDeviceToHost, s));
+    }
+    if (out_c) {
+        beta_table_kernel<<<grid, 256, 0, s>>>(sd, nullptr, n_groups, n_steps, static_cast<float *>(ctx->buf[B_BETA].p));
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaMemcpyAsync(out_c, ctx->buf[B_BETA].p, (size_t)cells * 4, cudaMemcpyDeviceToHost, s));
+    }
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return 0;
+}
+
 static int probe_common(mcq_ctx *ctx, int mode, int n, int q, int n_states, const uint8_t *states, int mem,
                         cudaStream_t s, KArgs &a) {
     if (!ctx) return fail(MCQ_EINVAL, "ctx is NULL");
@@ -659,7 +734,10 @@ int mcq_run(mcq_ctx *ctx, const mcq_run_params *p) {
         return fail(MCQ_EINVAL, "latin/klarner initialization assumes Q = N^2");
     const bool replay = p->replay_moves != nullptr;
     if (replay && (!p->replay_uniforms || !p->beta_f64)) return fail(MCQ_EINVAL, "replay needs replay_moves, replay_uniforms and beta_f64");
-    if (!replay && !p->beta_log2e && p->n_steps > 0) return fail(MCQ_EINVAL, "beta_log2e is NULL");
+    if (!replay && !p->schedules && !p->beta_f64 && p->n_steps > 0) return fail(MCQ_EINVAL, "a production run needs `schedules` (parameters) or `beta_f64` (a tabulated schedule)");
+    if (!replay && p->schedules)
+        for (int g = 0; g < p->n_groups; ++g)
+            if (p->schedules[g].type < MCQ_SCHED_CONSTANT || p->schedules[g].type > MCQ_SCHED_SINUSOIDAL) return fail(MCQ_EINVAL, "unknown schedule type");
     if (p->mem != MCQ_MEM_HOST && p->mem != MCQ_MEM_DEVICE) return fail(MCQ_EINVAL, "mem must be MCQ_MEM_HOST or MCQ_MEM_DEVICE");
     const bool want_hist = p->hist_dtype != MCQ_HIST_NONE && p->energy_history;
     const bool want_stats = p->stat_sum_e || p->stat_sum_e2;
@@ -776,7 +854,7 @@ int mcq_run(mcq_ctx *ctx, const mcq_run_params *p) {
             const size_t need = cta_smem(lpc);
             if (need > smem_block) return 0;
             // registers: the kernel is compiled for MCQ_SPEC_MINB CTAs of 4 warps per SM
-            return (int)std::min<size_t>((size_t)(MCQ_SPEC_MINB * 4 / w), smem_sm / (round_up((int)need, 1024) + 1024));
+            return (int)std::min<size_t>((size_t)((lpc == 32 ? MCQ_SPEC_MINB : 5) * 4 / w), smem_sm / (round_up((int)need, 1024) + 1024));
         };
         // relative throughput of one SM vs resident warps (measured, N=12 full_3d, single full wave)
         auto rate = [&](int lpc, int warps) {
@@ -834,17 +912,19 @@ int mcq_run(mcq_ctx *ctx, const mcq_run_params *p) {
     a.sl = sl;
     a.w_best = w_best; a.w_ring = w_ring; a.w_xch = w_xch;
     if (use_spec) {
-        DevBuf &nb = ctx->nbr[full * 256 + p->n];
-        if (!nb.p) {
+        const int nbr_key = full * 256 + p->n;
+        if (!ctx->nbr.count(nbr_key)) {   // registered only once it is allocated AND built
             const int cells = p->n * p->n * p->n;
-            if (nb.ensure((size_t)cells * sl.nbr_len * 2) || ctx->buf[B_MOVES].ensure((size_t)cells * sl.nbr_len * 2))
-                return fail(MCQ_ENOMEM, "device allocation failed (neighbour lists)");
+            DevBuf nb;
+            if (nb.ensure((size_t)cells * sl.nbr_len * 2)) return fail(MCQ_ENOMEM, "device allocation failed (neighbour lists)");
+            if (ctx->buf[B_MOVES].ensure((size_t)cells * sl.nbr_len * 2)) { nb.release(); return fail(MCQ_ENOMEM, "device allocation failed (neighbour lists)"); }
             build_neighbours_kernel<<<(cells + 127) / 128, 128, 0, s>>>(full, p->n, sl.nbr_len, full ? 2 : 1, static_cast<uint16_t *>(nb.p),
                                                                        static_cast<uint16_t *>(ctx->buf[B_MOVES].p));
-            CUDA_TRY(cudaGetLastError());
+            if (cudaError_t e = cudaGetLastError(); e != cudaSuccess) { nb.release(); return fail(MCQ_ECUDA, cudaGetErrorString(e)); }
+            ctx->nbr[nbr_key] = nb;
             ++launches;
         }
-        a.nbr = static_cast<const uint16_t *>(nb.p);
+        a.nbr = static_cast<const uint16_t *>(ctx->nbr[nbr_key].p);
         if (full) {
             DevBuf &gb = ctx->geo[p->n];
             if (!gb.p) {
@@ -871,18 +951,37 @@ int mcq_run(mcq_ctx *ctx, const mcq_run_params *p) {
         if (int rc = stage_in(ctx, B_RMOVES, p->replay_moves, (size_t)nc * ns * 4, mem, s, &d)) return rc; a.rmoves = static_cast<uint32_t *>(d);
         if (int rc = stage_in(ctx, B_RUNIF, p->replay_uniforms, (size_t)nc * ns * 8, mem, s, &d)) return rc; a.runif = static_cast<double *>(d);
     } else if (ns > 0) {
-        if (int rc = stage_in(ctx, B_BETA, p->beta_log2e, (size_t)p->n_groups * ns * 4, mem, s, &d)) return rc; a.beta_c = static_cast<float *>(d);
+        // production: the float32 table of -beta log2 e the fast path reads is built on the device, from the schedule
+        // parameters (experiments.py:13-77 evaluated in float64) or from the caller's float64 table of a closure;
+        // the float64 accept rule (accept.cuh) goes back to the same source
+        if (p->schedules) {
+            static_assert(sizeof(SchedDev) == sizeof(mcq_schedule), "schedule structs must match");
+            if (ctx->buf[B_SCHED].ensure((size_t)p->n_groups * sizeof(SchedDev))) return fail(MCQ_ENOMEM, "device allocation failed");
+            CUDA_TRY(cudaMemcpyAsync(ctx->buf[B_SCHED].p, p->schedules, (size_t)p->n_groups * sizeof(SchedDev), cudaMemcpyHostToDevice, s));
+            a.sched = static_cast<const SchedDev *>(ctx->buf[B_SCHED].p);
+        } else {
+            if (int rc = stage_in(ctx, B_BETA64, p->beta_f64, (size_t)p->n_groups * ns * 8, mem, s, &d)) return rc;
+            a.beta64 = static_cast<double *>(d);
+        }
+        const long long cells = (long long)p->n_groups * ns;
+        if (ctx->buf[B_BETA].ensure((size_t)cells * 4)) return fail(MCQ_ENOMEM, "device allocation failed (schedule table)");
+        beta_table_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, s>>>(a.sched, a.beta64, p->n_groups, ns, static_cast<float *>(ctx->buf[B_BETA].p));
+        CUDA_TRY(cudaGetLastError());
+        ++launches;
+        a.beta_c = static_cast<float *>(ctx->buf[B_BETA].p);
     }
+    a.band_abs = p->accept_all_f64 ? INFINITY : 4.0f;
 
     // ---- persistent record (always internal scratch; copied to the caller's arrays at the end) ----
-    // layout of B_REC: 9 int arrays of nc + 1 word for replay_err
-    if (ctx->buf[B_REC].ensure(((size_t)nc * 9 + 4) * 4)) return fail(MCQ_ENOMEM, "device allocation failed");
+    // layout of B_REC: 10 int arrays of nc + 1 word for replay_err
+    if (ctx->buf[B_REC].ensure(((size_t)nc * 10 + 4) * 4)) return fail(MCQ_ENOMEM, "device allocation failed");
     int *rec = static_cast<int *>(ctx->buf[B_REC].p);
     a.init_e = rec; a.cur_e = rec + nc; a.best_e = rec + 2 * (size_t)nc; a.best_step = rec + 3 * (size_t)nc;
     a.n_acc = rec + 4 * (size_t)nc; a.steps_done = rec + 5 * (size_t)nc; a.stale = rec + 6 * (size_t)nc;
     a.bin_mark = rec + 7 * (size_t)nc; a.near_cnt = reinterpret_cast<uint32_t *>(rec + 8 * (size_t)nc);
-    a.replay_err = reinterpret_cast<uint32_t *>(rec + 9 * (size_t)nc);
-    CUDA_TRY(cudaMemsetAsync(rec, 0, ((size_t)nc * 9 + 4) * 4, s));
+    a.flip_cnt = reinterpret_cast<uint32_t *>(rec + 9 * (size_t)nc);
+    a.replay_err = reinterpret_cast<uint32_t *>(rec + 10 * (size_t)nc);
+    CUDA_TRY(cudaMemsetAsync(rec, 0, ((size_t)nc * 10 + 4) * 4, s));
     if (ctx->buf[B_STATE].ensure((size_t)nc * sbytes) || ctx->buf[B_BEST].ensure((size_t)nc * sbytes)) return fail(MCQ_ENOMEM, "device allocation failed");
     a.state = static_cast<uint8_t *>(ctx->buf[B_STATE].p);
     a.best_state = static_cast<uint8_t *>(ctx->buf[B_BEST].p);
@@ -954,45 +1053,56 @@ int mcq_run(mcq_ctx *ctx, const mcq_run_params *p) {
         else if (mem == MCQ_MEM_HOST) CUDA_TRY(cudaMemcpyAsync(a.abits, p->accept_bits, (size_t)nc * abits_words * 4, cudaMemcpyHostToDevice, s));
     }
 
-    // ---- statistics accumulators ----
+    // ---- statistics accumulators (difference form while the chains run; integrated after the launches) ----
     unsigned long long *d_sum_e = nullptr, *d_sum_e2 = nullptr;
+    int *d_cnt = nullptr;
     const size_t stat_elems = (size_t)p->n_groups * ((size_t)ns + 1);
     if (want_stats) {
-        if (mem == MCQ_MEM_DEVICE) { d_sum_e = reinterpret_cast<unsigned long long *>(p->stat_sum_e); d_sum_e2 = reinterpret_cast<unsigned long long *>(p->stat_sum_e2); }
-        else {
-            if (ctx->buf[B_SUME].ensure(stat_elems * 8) || ctx->buf[B_SUME2].ensure(stat_elems * 8)) return fail(MCQ_ENOMEM, "device allocation failed");
+        if (mem == MCQ_MEM_DEVICE) {
+            d_sum_e = reinterpret_cast<unsigned long long *>(p->stat_sum_e); d_sum_e2 = reinterpret_cast<unsigned long long *>(p->stat_sum_e2);
+            d_cnt = p->stat_count;
+        } else {
+            if (ctx->buf[B_SUME].ensure(stat_elems * 8) || ctx->buf[B_SUME2].ensure(stat_elems * 8) ||
+                (p->stat_count && ctx->buf[B_SCNT].ensure(stat_elems * 4))) return fail(MCQ_ENOMEM, "device allocation failed");
             d_sum_e = static_cast<unsigned long long *>(ctx->buf[B_SUME].p);
             d_sum_e2 = static_cast<unsigned long long *>(ctx->buf[B_SUME2].p);
+            if (p->stat_count) d_cnt = static_cast<int *>(ctx->buf[B_SCNT].p);
         }
         if (!resume) {
             CUDA_TRY(cudaMemsetAsync(d_sum_e, 0, stat_elems * 8, s));
             CUDA_TRY(cudaMemsetAsync(d_sum_e2, 0, stat_elems * 8, s));
+            if (d_cnt) CUDA_TRY(cudaMemsetAsync(d_cnt, 0, stat_elems * 4, s));
         } else if (mem == MCQ_MEM_HOST) {
             CUDA_TRY(cudaMemcpyAsync(d_sum_e, p->stat_sum_e, stat_elems * 8, cudaMemcpyHostToDevice, s));
             CUDA_TRY(cudaMemcpyAsync(d_sum_e2, p->stat_sum_e2, stat_elems * 8, cudaMemcpyHostToDevice, s));
+            if (d_cnt) CUDA_TRY(cudaMemcpyAsync(d_cnt, p->stat_count, stat_elems * 4, cudaMemcpyHostToDevice, s));
         }
+        a.dsum_e = d_sum_e; a.dsum_e2 = d_sum_e2; a.dcount = d_cnt; a.stat_pitch = (long long)ns + 1;
+        a.stat_rows32 = (long long)p->n_groups * ((long long)ns + 1) < (1LL << 31);
     }
 
     // ---- history plan ----
     int hkind = MCQ_HIST_NONE;
     if (want_hist) hkind = p->hist_dtype;
-    else if (want_stats) hkind = e_max < 65536 ? MCQ_HIST_U16 : MCQ_HIST_I32;
     const size_t esz = hkind == MCQ_HIST_U16 ? 2 : 4;
     const bool direct = want_hist && mem == MCQ_MEM_DEVICE;  // kernel writes the caller's array itself
     int chunk = ns > 0 ? ns : 1;
     if (hkind != MCQ_HIST_NONE && !direct) {
         if (p->chunk_steps > 0) chunk = p->chunk_steps;
         else {
-            const size_t budget = (size_t)1 << 30;  // per buffer
+            const size_t budget = (size_t)1 << 29;  // per buffer (there are two)
             size_t c = budget / ((size_t)nc * esz);
             chunk = (int)std::min<size_t>(std::max<size_t>(c, 64), (size_t)std::max(ns, 1));
         }
     } else if (p->chunk_steps > 0) chunk = p->chunk_steps;
     chunk = std::max(HBLK, chunk / HBLK * HBLK);
     const long long chunk_pitch = ((long long)chunk + 1 + 7) / 8 * 8;   // rows stay 16-byte aligned
-    if (hkind != MCQ_HIST_NONE && !direct) {
+    // host histories: two chunk buffers, so that the D2H copy of chunk k (copy stream) runs under the kernel of chunk k+1
+    const bool staged = hkind != MCQ_HIST_NONE && !direct;
+    const bool two_bufs = staged && (long long)chunk < (long long)(t_stop - t_start);
+    if (staged) {
         const size_t bytes = (size_t)nc * chunk_pitch * esz;
-        if (ctx->buf[B_HIST0].ensure(bytes)) return fail(MCQ_ENOMEM, "device allocation failed (history chunk)");
+        if (ctx->buf[B_HIST0].ensure(bytes) || (two_bufs && ctx->buf[B_HIST1].ensure(bytes))) return fail(MCQ_ENOMEM, "device allocation failed (history chunk)");
     }
 
     // ---- the launches ----
@@ -1007,22 +1117,31 @@ int mcq_run(mcq_ctx *ctx, const mcq_run_params *p) {
     if (const char *e = getenv("MCQ_STREAMS")) n_sub = std::max(1, std::min(4, std::min(atoi(e), grid)));
     cudaStream_t sub_stream[4];
     for (int b = 0; b < n_sub; ++b) sub_stream[b] = n_sub == 1 ? s : ctx->sub_stream[b];
-    cudaEvent_t e_start, e_end, e_sub[4];
-    CUDA_TRY(cudaEventCreate(&e_start));
-    CUDA_TRY(cudaEventCreate(&e_end));
+    EventBag events;
+    cudaEvent_t e_start, e_end, e_sub[4], e_kernel[2], e_copy[2];
+    CUDA_TRY(events.make(&e_start, cudaEventDefault));
+    CUDA_TRY(events.make(&e_end, cudaEventDefault));
     CUDA_TRY(cudaEventRecord(e_start, s));
     for (int b = 0; b < n_sub && n_sub > 1; ++b) {
-        CUDA_TRY(cudaEventCreateWithFlags(&e_sub[b], cudaEventDisableTiming));
+        CUDA_TRY(events.make(&e_sub[b], cudaEventDisableTiming));
         CUDA_TRY(cudaStreamWaitEvent(sub_stream[b], e_start, 0));
     }
-    for (int t0 = t_start, first_pass = 1; t0 < t_stop || first_pass; first_pass = 0) {
+    const bool overlap_copy = two_bufs && n_sub == 1;
+    for (int b = 0; b < 2 && overlap_copy; ++b) {
+        CUDA_TRY(events.make(&e_kernel[b], cudaEventDisableTiming));
+        CUDA_TRY(events.make(&e_copy[b], cudaEventDisableTiming));
+    }
+    int chunk_no = 0;
+    for (int t0 = t_start, first_pass = 1; t0 < t_stop || first_pass; first_pass = 0, ++chunk_no) {
         const int t1 = std::min(t_stop, t0 + chunk);
+        const int hb = overlap_copy ? (chunk_no & 1) : 0;   // history buffer of this chunk
         a.t_begin = t0; a.t_end = t1;
         a.hist_kind = hkind;
         if (hkind != MCQ_HIST_NONE) {
             if (direct) { a.hist = p->energy_history; a.hist_pitch = p->hist_pitch; a.h_origin = 0; }
-            else { a.hist = ctx->buf[B_HIST0].p; a.hist_pitch = chunk_pitch; a.h_origin = t0 == 0 ? 0 : (long long)t0 + 1; }
+            else { a.hist = ctx->buf[hb ? B_HIST1 : B_HIST0].p; a.hist_pitch = chunk_pitch; a.h_origin = t0 == 0 ? 0 : (long long)t0 + 1; }
         }
+        if (overlap_copy && chunk_no >= 2) CUDA_TRY(cudaStreamWaitEvent(s, e_copy[hb], 0));   // the buffer's previous chunk has left
         a.bin_at_begin = 0;
         if (p->n_bins > 0) {
             // the bin that was still open when the previous launch ended (the kernels close a bin
@@ -1044,40 +1163,36 @@ int mcq_run(mcq_ctx *ctx, const mcq_run_params *p) {
                      : use_wide ? launch_wide(wide_threads, a, cta_hi - cta_lo, smem, sb)
                                 : launch_anneal(G, a, replay, cta_hi - cta_lo, block, smem, sb));
             ++launches;
-            if (want_stats && n_cols > 0) {
-                const char *hb = direct ? static_cast<const char *>(p->energy_history) + (size_t)h0 * esz : static_cast<const char *>(a.hist);
-                const long long hp = direct ? p->hist_pitch : chunk_pitch;
-                hb += (size_t)lo * hp * esz;
-                const int n = hi - lo;
-                const int *grp = a.group ? a.group + lo : nullptr;
-                // 16-byte column vectors when rows and the tile start are aligned (always true for the chunk buffer)
-                const bool vec_ok = (hp * esz) % 16 == 0 && (reinterpret_cast<uintptr_t>(hb) % 16) == 0;
-                const int vec = vec_ok ? (int)(16 / esz) : 1;
-                dim3 sg((n_cols + 128 * vec - 1) / (128 * vec), std::max(1, std::min(64, n / 64)));
-                if (hkind == MCQ_HIST_U16) {
-                    const uint16_t *h16 = reinterpret_cast<const uint16_t *>(hb);
-                    if (vec_ok) stats_kernel<uint16_t, 8><<<sg, 128, 0, sb>>>(h16, hp, n_cols, h0, n, grp, a.steps_done + lo, d_sum_e, d_sum_e2, (long long)ns + 1);
-                    else stats_kernel<uint16_t, 1><<<sg, 128, 0, sb>>>(h16, hp, n_cols, h0, n, grp, a.steps_done + lo, d_sum_e, d_sum_e2, (long long)ns + 1);
-                } else {
-                    const int *h32 = reinterpret_cast<const int *>(hb);
-                    if (vec_ok) stats_kernel<int, 4><<<sg, 128, 0, sb>>>(h32, hp, n_cols, h0, n, grp, a.steps_done + lo, d_sum_e, d_sum_e2, (long long)ns + 1);
-                    else stats_kernel<int, 1><<<sg, 128, 0, sb>>>(h32, hp, n_cols, h0, n, grp, a.steps_done + lo, d_sum_e, d_sum_e2, (long long)ns + 1);
-                }
-                CUDA_TRY(cudaGetLastError());
-                ++launches;
-            }
             if (want_hist && !direct && n_cols > 0) {
+                cudaStream_t sc = sb;
+                if (overlap_copy) {   // copy on the copy stream, ordered after this chunk's kernel
+                    sc = ctx->copy_stream;
+                    CUDA_TRY(cudaEventRecord(e_kernel[hb], sb));
+                    CUDA_TRY(cudaStreamWaitEvent(sc, e_kernel[hb], 0));
+                }
                 CUDA_TRY(cudaMemcpy2DAsync(static_cast<char *>(p->energy_history) + ((size_t)lo * p->hist_pitch + (size_t)h0) * esz,
                                            (size_t)p->hist_pitch * esz, static_cast<const char *>(a.hist) + (size_t)lo * chunk_pitch * esz,
-                                           (size_t)chunk_pitch * esz, (size_t)n_cols * esz, hi - lo, cudaMemcpyDeviceToHost, sb));
+                                           (size_t)chunk_pitch * esz, (size_t)n_cols * esz, hi - lo, cudaMemcpyDeviceToHost, sc));
+                if (overlap_copy) CUDA_TRY(cudaEventRecord(e_copy[hb], sc));
             }
         }
         t0 = t1;
     }
+    for (int b = 0; b < 2 && overlap_copy && b < chunk_no; ++b) CUDA_TRY(cudaStreamWaitEvent(s, e_copy[b], 0));
     a.chain_begin = 0; a.n_chains = nc;
     for (int b = 0; b < n_sub && n_sub > 1; ++b) {
         CUDA_TRY(cudaEventRecord(e_sub[b], sub_stream[b]));
         CUDA_TRY(cudaStreamWaitEvent(s, e_sub[b], 0));
+    }
+    if (want_stats) {   // differences -> sums over the columns this call produced: history indices [t_start + 1 (or 0), t_stop]
+        const long long h0 = t_start == 0 ? 0 : (long long)t_start + 1, h1 = t_stop;
+        if (h1 >= h0) {
+            stat_integrate_kernel<unsigned long long><<<p->n_groups, 1024, 0, s>>>(d_sum_e, (long long)ns + 1, h0, h1);
+            stat_integrate_kernel<unsigned long long><<<p->n_groups, 1024, 0, s>>>(d_sum_e2, (long long)ns + 1, h0, h1);
+            if (d_cnt) stat_integrate_kernel<int><<<p->n_groups, 1024, 0, s>>>(d_cnt, (long long)ns + 1, h0, h1);
+            CUDA_TRY(cudaGetLastError());
+            launches += d_cnt ? 3 : 2;
+        }
     }
     CUDA_TRY(cudaEventRecord(e_end, s));
 
@@ -1089,6 +1204,7 @@ int mcq_run(mcq_ctx *ctx, const mcq_run_params *p) {
     if (int rc = copy_out(p->n_accepted, a.n_acc, (size_t)nc * 4, mem, s)) return rc;
     if (int rc = copy_out(p->steps_done, a.steps_done, (size_t)nc * 4, mem, s)) return rc;
     if (int rc = copy_out(p->n_near_threshold, a.near_cnt, (size_t)nc * 4, mem, s)) return rc;
+    if (int rc = copy_out(p->n_fp32_flips, a.flip_cnt, (size_t)nc * 4, mem, s)) return rc;
     if (int rc = copy_out(p->record_out, rec, (size_t)nc * MCQ_RECORD_INTS * 4, mem, s)) return rc;
     if (int rc = copy_out(p->final_state, a.state, (size_t)nc * sbytes, mem, s)) return rc;
     if (int rc = copy_out(p->best_state, a.best_state, (size_t)nc * sbytes, mem, s)) return rc;
@@ -1098,6 +1214,7 @@ int mcq_run(mcq_ctx *ctx, const mcq_run_params *p) {
         if (want_stats) {
             CUDA_TRY(cudaMemcpyAsync(p->stat_sum_e, d_sum_e, stat_elems * 8, cudaMemcpyDeviceToHost, s));
             CUDA_TRY(cudaMemcpyAsync(p->stat_sum_e2, d_sum_e2, stat_elems * 8, cudaMemcpyDeviceToHost, s));
+            if (d_cnt) CUDA_TRY(cudaMemcpyAsync(p->stat_count, d_cnt, stat_elems * 4, cudaMemcpyDeviceToHost, s));
         }
     }
     uint32_t h_err = 0;
@@ -1105,8 +1222,6 @@ int mcq_run(mcq_ctx *ctx, const mcq_run_params *p) {
     CUDA_TRY(cudaStreamSynchronize(s));
     float ms_total = 0.f;
     CUDA_TRY(cudaEventElapsedTime(&ms_total, e_start, e_end));   // device span of all launches of this call
-    cudaEventDestroy(e_start); cudaEventDestroy(e_end);
-    for (int b = 0; b < n_sub && n_sub > 1; ++b) cudaEventDestroy(e_sub[b]);
     if (p->kernel_ms) *p->kernel_ms = ms_total;
     if (p->gpu_launches) *p->gpu_launches = launches;
     if (replay && h_err) return fail(MCQ_EREPLAY, "replayed stream contained an illegal proposal (occupied cell, same height or out of range)");

@@ -1,6 +1,6 @@
 // Philox4x32-10 counter-based generator (Salmon, Moraes, Dror, Shaw -- SC'11).
 // One call turns (counter[4], key[2]) into four uniform 32-bit words; there is no state, so a
-// chain's stream depends only on its key (the chain seed) and the step index, never on which
+// chain's stream depends only on the chain seed and the step index, never on which
 // GPU / CTA / lane runs it.  The reference draws from NumPy's global MT19937 instead
 // (experiments.py:221-239, :311-327); parity under independent RNG is statistical.
 #pragma once
@@ -44,7 +44,19 @@ MCQ_HD Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
     return o;
 }
 
-// counter domains (c3): keeps the streams of different uses of one chain key disjoint
-enum : uint32_t { PHILOX_DOMAIN_STEP = 0u, PHILOX_DOMAIN_INIT = 1u };
+// How a chain draws its words.  The chain's 64-bit seed sits in the COUNTER, the cipher key is a constant:
+//     chain_words(i, seed, stream) = Philox4x32-10(counter = (i, seed_lo, seed_hi, stream), key = CHAIN_KEY)
+// so the ten round keys are immediates in the compiled code (no per-chain key registers, no key arithmetic) and
+// a chain's words still depend on (seed, i, stream) only.  Streams of a step i = s:
+//     0               the step's four words (proposal, uniform)
+//     1 + k           further candidate cells of a full_3d proposal (k = 0, 1, ...)
+//     0x80000000      low bits of the step's 53-bit uniform (float64 accept rule)
+// and of the initial state (i = block of four words): 0x40000000.
+constexpr uint32_t CHAIN_KEY0 = 0x243F6A88u, CHAIN_KEY1 = 0x85A308D3u;   // first 64 fractional bits of pi
+enum : uint32_t { PHILOX_STREAM_STEP = 0u, PHILOX_STREAM_INIT = 0x40000000u, PHILOX_STREAM_UNIFORM_LO = 0x80000000u };
+
+MCQ_HD Philox4 chain_words(uint32_t i, uint32_t seed_lo, uint32_t seed_hi, uint32_t stream) {
+    return philox4x32_10(i, seed_lo, seed_hi, stream, CHAIN_KEY0, CHAIN_KEY1);
+}
 
 }  // namespace mcq

@@ -297,18 +297,12 @@ __device__ __forceinline__ T *ptr_mad(T *base, uint32_t idx, uint32_t scale) {
     return reinterpret_cast<T *>(r);
 }
 
-__device__ __forceinline__ float ex2_approx(float x) {
-    float y;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-
 // One lane group of LPC lanes (32 or 16) owns a chain; a warp carries 32/LPC chains.  Narrower
 // groups waste fewer evaluated proposals per round (at 3 % acceptance a 16-lane group commits
 // 12.9 of 16, a 32-lane group 20.7 of 32); committed moves are applied by the whole warp, one
 // chain after the other, so the table update keeps 32 lanes busy either way.
 template <bool FULL, bool REPLAY, bool EARLY, int NR, int LPC, int CN = 0, int HK = -1>
-__global__ void __launch_bounds__(128, MCQ_SPEC_MINB) spec_kernel(const __grid_constant__ KArgs a) {
+__global__ void __launch_bounds__(128, LPC == 32 ? MCQ_SPEC_MINB : 5) spec_kernel(const __grid_constant__ KArgs a) {
     constexpr unsigned FULLMASK = 0xffffffffu;
     constexpr int NF = FULL ? NFAM : NFAM - 1;
     // full_3d: 16-bit table entries whose top bit says "a queen stands here", so the occupancy test of a
@@ -326,7 +320,9 @@ __global__ void __launch_bounds__(128, MCQ_SPEC_MINB) spec_kernel(const __grid_c
     const int N = SpecGeom<FULL, CN>::n(a), Q = SpecGeom<FULL, CN>::q(a);
     const SLayout sl = SpecGeom<FULL, CN>::layout(a);
     const int state_bytes = FULL ? 3 * Q : Q;
-    const int hist_kind = HK >= 0 ? HK : a.hist_kind;   // HK: history element kind compiled in (0 none, 1 uint16)
+    // HK: history kind compiled in: 0 none, 1 uint16, 3 none + cross-replica statistics (difference form); < 0: run time
+    const int hist_kind = HK == 3 ? 0 : HK >= 0 ? HK : a.hist_kind;
+    const bool stats_rt = HK < 0 && a.dsum_e != nullptr;   // generic kernels: statistics behind the rare branch
 
     // ---- CTA-shared geometry: shared-line bits at offset 0, cell -> wide id at sl.off_wide ----
     if (FULL) {
@@ -383,8 +379,17 @@ __global__ void __launch_bounds__(128, MCQ_SPEC_MINB) spec_kernel(const __grid_c
     }
 
     // ---- persistent record (every lane of a group holds its chain's scalars) ----
-    int best = E, stale = 0, n_acc = 0, best_step = 0, bin_mark = 0;
+    // best_step, the open acceptance bin and its mark are only touched behind the rare branch: they live in the
+    // slab's record words (sR + 0, 4, 8), not in registers
+    const int sR = sT + sl.off_rec;
+    int best = E, stale = 0, n_acc = 0;
     int done = a.t_end;
+    {
+        int best_step0 = 0, bin_mark0 = 0;
+        if (live && a.t_begin != 0) { best_step0 = a.best_step[chain]; bin_mark0 = a.bin_mark[chain]; }
+        if (sub == 0) { SM32(sR) = (uint32_t)best_step0; SM32(sR + 4) = (uint32_t)a.bin_at_begin; SM32(sR + 8) = (uint32_t)bin_mark0; }
+        __syncwarp();
+    }
     int t = live ? a.t_begin : a.t_end;
     if (live) {
         if (a.t_begin == 0) {
@@ -392,13 +397,12 @@ __global__ void __launch_bounds__(128, MCQ_SPEC_MINB) spec_kernel(const __grid_c
                 if (a.init_e) a.init_e[chain] = E;
                 if (hist_kind == 1) reinterpret_cast<uint16_t *>(a.hist)[(size_t)chain * a.hist_pitch] = (uint16_t)E;
                 else if (hist_kind == 2) reinterpret_cast<int *>(a.hist)[(size_t)chain * a.hist_pitch] = E;
+                if (HK == 3 || stats_rt) stat_delta(a, a.group ? a.group[chain] : 0, 0, 0, E, 1);
             }
         } else {
             best = a.best_e[chain];
             stale = a.stale[chain];
             n_acc = a.n_acc[chain];
-            best_step = a.best_step[chain];
-            bin_mark = a.bin_mark[chain];
             const int sd = a.steps_done[chain];
             if (sd < a.t_begin) { done = sd; t = a.t_end; }   // stopped in an earlier launch
         }
@@ -410,15 +414,17 @@ __global__ void __launch_bounds__(128, MCQ_SPEC_MINB) spec_kernel(const __grid_c
     const double *beta64_row = REPLAY ? a.beta64 + (size_t)grp * a.n_steps : nullptr;
     const uint32_t *mv_row = REPLAY ? a.rmoves + (size_t)chain_c * a.n_steps : nullptr;
     const double *un_row = REPLAY ? a.runif + (size_t)chain_c * a.n_steps : nullptr;
-    int bin = a.bin_at_begin;
-    int next_edge = a.n_bins > 0 ? a.bin_starts[bin + 1] : 0x7fffffff;
+    int next_edge = a.n_bins > 0 ? a.bin_starts[a.bin_at_begin + 1] : 0x7fffffff;
+    // statistics in difference form (KArgs::dsum_e): this chain's group row of sum E; sum E^2 sits at a fixed distance
+    // (HK == 3 is only dispatched when n_groups * (n_steps + 1) fits 31 bits)
+    [[maybe_unused]] const uint32_t srow = HK == 3 ? (uint32_t)grp * (uint32_t)a.stat_pitch : 0u;
     const int sG = sT + sl.off_ring;   // ring of random words: 64 steps x 16 B
     [[maybe_unused]] int tfill = t;       // steps < tfill of this chain have their words in the ring
     [[maybe_unused]] uint32_t near = 0u;
     // history row, addressed by history index h = step + 1 (h_origin = index held by column 0)
     unsigned char *hrow = static_cast<unsigned char *>(a.hist) +
                           ((long long)chain_c * a.hist_pitch - a.h_origin) * (hist_kind == 1 ? 2 : 4);
-    uint32_t *abits_row = a.abits ? a.abits + (size_t)chain_c * a.abits_pitch : nullptr;
+    const bool want_abits = a.abits != nullptr;
 
     while (CPW == 1 ? t < a.t_end : __any_sync(FULLMASK, t < a.t_end)) {
         const bool active = CPW == 1 || t < a.t_end;
@@ -431,6 +437,7 @@ __global__ void __launch_bounds__(128, MCQ_SPEC_MINB) spec_kernel(const __grid_c
         int dE;
         bool accept;
         [[maybe_unused]] bool bad = false, near_flag = false;
+        [[maybe_unused]] unsigned nearm = 0u, flipm = 0u;   // production: lanes of this group decided by the float64 rule / flipped by it
         if constexpr (REPLAY) {
             const uint32_t mv = mv_row[s];
             const double u64 = un_row[s], b64 = beta64_row[s];
@@ -466,7 +473,7 @@ __global__ void __launch_bounds__(128, MCQ_SPEC_MINB) spec_kernel(const __grid_c
             // steps it commits, so one Philox4x32-10 call per lane refills LPC steps that are all used,
             // instead of recomputing the discarded lanes' words every round.
             if (active && tfill < t + LPC) {
-                const Philox4 w = philox4x32_10((uint32_t)(tfill + sub), 0u, 0u, PHILOX_DOMAIN_STEP, key0, key1);
+                const Philox4 w = chain_words((uint32_t)(tfill + sub), key0, key1, PHILOX_STREAM_STEP);
                 asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(sbase + (uint32_t)(sG + 16 * ((tfill + sub) & 63))),
                              "r"(w.x), "r"(w.y), "r"(w.z), "r"(w.w) : "memory");
                 tfill += LPC;
@@ -494,7 +501,7 @@ __global__ void __launch_bounds__(128, MCQ_SPEC_MINB) spec_kernel(const __grid_c
                     v1 = (int)(TE)TBL(sT, c1);
                     int e = 0;
                     while (v1 & OCC) {
-                        const Philox4 r2 = philox4x32_10((uint32_t)s, 0u, 1u + (uint32_t)(e >> 2), PHILOX_DOMAIN_STEP, key0, key1);
+                        const Philox4 r2 = chain_words((uint32_t)s, key0, key1, 1u + (uint32_t)(e >> 2));
                         const int sel = e & 3;
                         c1 = __umulhi(sel == 0 ? r2.x : sel == 1 ? r2.y : sel == 2 ? r2.z : r2.w, N3);
                         v1 = (int)(TE)TBL(sT, c1);
@@ -517,10 +524,21 @@ __global__ void __launch_bounds__(128, MCQ_SPEC_MINB) spec_kernel(const __grid_c
                 dE = (int)(TE)TBL(sT, c1) - (int)(TE)TBL(sT, c0) + 1;
                 aux = ij | (k1 << 16);
             }
-            // Metropolis (experiments.py:238-239 / :326-327): u < exp(-beta dE), u = word / 2^32
-            const float p = ex2_approx(cb * (float)dE);
-            const uint32_t thr = __float2uint_rz(p * 4294967296.0f);   // saturates at 2^32 - 1
-            accept = (dE <= 0) || (r.z < thr);
+            // Metropolis (experiments.py:238-239 / :326-327): float32 decision, retaken with the float64 rule when the
+            // uniform word lies inside the float32 error band of the threshold (accept.cuh)
+            bool near_band;
+            metropolis_fast(dE, cb, r.z, a.band_abs, accept, near_band);
+            if (__any_sync(FULLMASK, near_band)) {   // rare: about 1e-4 of the rounds
+                bool flip = false;
+                near_band = near_band && valid;
+                if (near_band) {
+                    const bool exact = metropolis_exact(a.sched, a.beta64, a.n_steps, a.group ? a.group[chain_c] : 0, key0, key1, s, dE, r.z);
+                    flip = exact != accept;
+                    accept = exact;
+                }
+                nearm = (__ballot_sync(FULLMASK, near_band) >> (half * LPC)) & LMASK;
+                flipm = (__ballot_sync(FULLMASK, flip) >> (half * LPC)) & LMASK;
+            }
         }
         accept = accept && valid;
 
@@ -618,9 +636,32 @@ __global__ void __launch_bounds__(128, MCQ_SPEC_MINB) spec_kernel(const __grid_c
         }
         // ---------------- bookkeeping; everything infrequent sits behind ONE branch ----------------
         const int n_before = n_acc;
+        if constexpr (HK == 3) {
+            // sum E / sum E^2 over the replicas of a group, difference form: an accepted move adds dE and
+            // E_new^2 - E_old^2 to the column of the history index it produces (one lane, two reductions)
+            if (has && sub == 0 && E_new != E) {
+                const long long de = (long long)(E_new - E);
+                unsigned long long *pe = a.dsum_e + (srow + (uint32_t)(t + first + 1));
+                atomicAdd(pe, (unsigned long long)de);
+                atomicAdd(pe + (a.dsum_e2 - a.dsum_e), (unsigned long long)(de * (long long)(E_new + E)));
+            }
+        }
+        const int E_old = E;
         if (has) { E = E_new; ++n_acc; }
         const bool edge = active && t + adv - 1 >= next_edge;
-        if (edge || improved || stop || (has && abits_row != nullptr)) {
+        if (edge || improved || stop || (has && (want_abits || stats_rt)) || (!REPLAY && nearm != 0u)) {
+            int bin = (int)SM32(sR + 4).get(), bin_mark = (int)SM32(sR + 8).get();
+            if constexpr (!REPLAY) {
+                if (nearm) {   // band decisions among the steps this round consumed
+                    const unsigned committed = adv >= 32 ? FULLMASK : ((1u << adv) - 1u);
+                    if (sub == 0 && a.near_cnt) atomicAdd(a.near_cnt + chain, (unsigned)__popc(nearm & committed));
+                    if (sub == 0 && a.flip_cnt && (flipm & committed)) atomicAdd(a.flip_cnt + chain, (unsigned)__popc(flipm & committed));
+                }
+            }
+            if (stats_rt && sub == 0) {
+                if (has && E != E_old) stat_delta(a, a.group ? a.group[chain] : 0, (long long)t + first + 1, E_old, E, 0);
+                if (stop) stat_delta(a, a.group ? a.group[chain] : 0, (long long)t + adv, E, 0, -1);
+            }
             // acceptance bins: close every bin that ends at or before the last consumed step (an accept
             // of this round belongs to the bin its step lies in, i.e. the one that stays open)
             while (active && t + adv - 1 >= next_edge) {
@@ -631,11 +672,11 @@ __global__ void __launch_bounds__(128, MCQ_SPEC_MINB) spec_kernel(const __grid_c
             }
             if (has) {
                 const int ta = t + first;
-                if (sub == 0 && abits_row) atomicOr(abits_row + (ta >> 5), 1u << (ta & 31));
+                if (sub == 0 && want_abits) atomicOr(a.abits + (size_t)chain * a.abits_pitch + (ta >> 5), 1u << (ta & 31));
                 if (improved) {
                     // snapshot: the state at the first visit of the minimum (strict <, :252 / :340)
                     best = E;
-                    if (!stop) best_step = ta + 1;
+                    if (!stop && sub == 0) SM32(sR) = (uint32_t)(ta + 1);
                     uint8_t *bs = a.best_state + (size_t)chain * state_bytes;
                     if (FULL) {
                         for (int qi = sub; qi < Q; qi += LPC) {
@@ -651,6 +692,7 @@ __global__ void __launch_bounds__(128, MCQ_SPEC_MINB) spec_kernel(const __grid_c
                 done = t + adv - 1;
                 if (sub == 0 && a.acc_hist) a.acc_hist[(size_t)chain * a.n_bins + bin] = (uint32_t)(n_acc - bin_mark);
             }
+            if (edge && sub == 0) { SM32(sR + 4) = (uint32_t)bin; SM32(sR + 8) = (uint32_t)bin_mark; }
         }
         t = stop ? a.t_end : t + adv;   // a stopped chain is finished; the other groups of the warp go on
     }
@@ -659,11 +701,12 @@ __global__ void __launch_bounds__(128, MCQ_SPEC_MINB) spec_kernel(const __grid_c
     __syncwarp();
     if (!live) return;
     if (sub == 0) {
+        const int bin = (int)SM32(sR + 4).get(), bin_mark = (int)SM32(sR + 8).get();
         if (a.t_end == a.n_steps && a.n_bins > 0 && a.acc_hist && done == a.t_end)
             a.acc_hist[(size_t)chain * a.n_bins + bin] = (uint32_t)(n_acc - bin_mark);
         a.cur_e[chain] = E;
         a.best_e[chain] = best;
-        a.best_step[chain] = best_step;
+        a.best_step[chain] = (int)SM32(sR).get();
         a.n_acc[chain] = n_acc;
         a.stale[chain] = stale;
         a.bin_mark[chain] = bin_mark;

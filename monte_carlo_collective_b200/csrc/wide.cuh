@@ -119,6 +119,7 @@ __global__ void __launch_bounds__(NT, 1) wide_kernel(const __grid_constant__ KAr
             if (a.init_e) a.init_e[chain] = E;
             if (a.hist_kind == 1) reinterpret_cast<uint16_t *>(a.hist)[(size_t)chain * a.hist_pitch] = (uint16_t)E;
             else if (a.hist_kind == 2) reinterpret_cast<int *>(a.hist)[(size_t)chain * a.hist_pitch] = E;
+            if (a.dsum_e) stat_delta(a, a.group ? a.group[chain] : 0, 0, 0, E, 1);
         }
     } else {
         best = a.best_e[chain];
@@ -131,7 +132,9 @@ __global__ void __launch_bounds__(NT, 1) wide_kernel(const __grid_constant__ KAr
     }
     const unsigned long long sd64 = a.seeds ? a.seeds[chain] : 0ull;
     const uint32_t key0 = (uint32_t)sd64, key1 = (uint32_t)(sd64 >> 32);
-    const float *beta_row = a.beta_c + (size_t)(a.group ? a.group[chain] : 0) * a.n_steps;
+    const int grp = a.group ? a.group[chain] : 0;
+    const float *beta_row = a.beta_c + (size_t)grp * a.n_steps;
+    uint32_t near = 0u, flips = 0u;   // this thread's band decisions among the consumed steps
     int bin = a.bin_at_begin;
     int next_edge = a.n_bins > 0 ? a.bin_starts[bin + 1] : NONE;
     int tfill = t;
@@ -143,7 +146,7 @@ __global__ void __launch_bounds__(NT, 1) wide_kernel(const __grid_constant__ KAr
     while (t < a.t_end) {
         // ---------------- random words: refill the ring when this round would read past it ----------------
         if (tfill < t + NT) {
-            const Philox4 w = philox4x32_10((uint32_t)(tfill + tid), 0u, 0u, PHILOX_DOMAIN_STEP, key0, key1);
+            const Philox4 w = chain_words((uint32_t)(tfill + tid), key0, key1, PHILOX_STREAM_STEP);
             ring[(tfill + tid) & (RING - 1)] = make_uint4(w.x, w.y, w.z, w.w);
             tfill += NT;
             cta_sync();
@@ -156,7 +159,7 @@ __global__ void __launch_bounds__(NT, 1) wide_kernel(const __grid_constant__ KAr
 
         // ---------------- this thread's proposal: step s against the current state ----------------
         int i0 = 0, j0 = 0, k0c = 0, i1 = 0, j1 = 0, k1c = 0, qsel = 0, dE = 0;
-        bool accept = false;
+        bool accept = false, was_near = false, was_flip = false;
         if (tid < width) {
         if constexpr (FULL) {
             qsel = (int)__umulhi(w.x, (uint32_t)a.Q);
@@ -171,7 +174,7 @@ __global__ void __launch_bounds__(NT, 1) wide_kernel(const __grid_constant__ KAr
                 else if (tries == 1) word = w.x * (uint32_t)a.Q;   // what the queen draw left of word x
                 else {
                     const int e = tries - 2;
-                    const Philox4 r = philox4x32_10((uint32_t)s, 0u, 1u + (uint32_t)(e >> 2), PHILOX_DOMAIN_STEP, key0, key1);
+                    const Philox4 r = chain_words((uint32_t)s, key0, key1, 1u + (uint32_t)(e >> 2));
                     const int sel = e & 3;
                     word = sel == 0 ? r.x : sel == 1 ? r.y : sel == 2 ? r.z : r.w;
                 }
@@ -205,9 +208,15 @@ __global__ void __launch_bounds__(NT, 1) wide_kernel(const __grid_constant__ KAr
             }
         }
         // Metropolis (experiments.py:238-239 / :326-327): u < exp(-beta dE), u = word / 2^32
-        const float p = exp2f(cb * (float)dE);
-        const uint32_t thr = __float2uint_rz(p * 4294967296.0f);   // saturates at 2^32 - 1
-        accept = valid && ((dE <= 0) || (w.z < thr));
+        bool near_band;
+        metropolis_fast(dE, cb, w.z, a.band_abs, accept, near_band);
+        if (near_band && valid) {   // inside the float32 error band: the float64 rule decides (accept.cuh)
+            const bool exact = metropolis_exact(a.sched, a.beta64, a.n_steps, grp, key0, key1, s, dE, w.z);
+            was_near = true;
+            was_flip = exact != accept;
+            accept = exact;
+        }
+        accept = accept && valid;
         }
 
         // ---------------- the CTA commits its first accepted proposal ----------------
@@ -247,6 +256,7 @@ __global__ void __launch_bounds__(NT, 1) wide_kernel(const __grid_constant__ KAr
             }
         }
         const bool has = first >= 0;
+        if (was_near && tid < adv) { ++near; flips += (uint32_t)was_flip; }
         // history: steps t .. t+adv_h-1; all but an accepted last one keep the old energy
         if (tid < adv_h && a.hist_kind) {
             const int v = (tid == first) ? E_new : E;
@@ -294,6 +304,10 @@ __global__ void __launch_bounds__(NT, 1) wide_kernel(const __grid_constant__ KAr
 
         // ---------------- bookkeeping ----------------
         const int n_before = n_acc;
+        if (a.dsum_e && tid == 0) {   // statistics in difference form (KArgs::dsum_e)
+            if (has && E_new != E) stat_delta(a, grp, (long long)t + first + 1, E, E_new, 0);
+            if (stop) stat_delta(a, grp, (long long)t + adv, has ? E_new : E, 0, -1);   // nothing is appended from here on
+        }
         if (has) { E = E_new; ++n_acc; jfresh = false; }
         if (t + adv - 1 >= next_edge || improved || stop || (has && abits_row != nullptr)) {
             // acceptance bins: close every bin that ends at or before the last consumed step
@@ -339,6 +353,8 @@ __global__ void __launch_bounds__(NT, 1) wide_kernel(const __grid_constant__ KAr
 
     // ---------------- write the record back ----------------
     __syncthreads();
+    if (near && a.near_cnt) atomicAdd(a.near_cnt + chain, near);
+    if (flips && a.flip_cnt) atomicAdd(a.flip_cnt + chain, flips);
     if (tid == 0) {
         if (a.t_end == a.n_steps && a.n_bins > 0 && a.acc_hist && done == a.t_end)
             a.acc_hist[(size_t)chain * a.n_bins + bin] = (uint32_t)(n_acc - bin_mark);

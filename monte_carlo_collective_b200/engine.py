@@ -81,7 +81,9 @@ class RunResult:
     stat_sum_e: object = None         # [n_groups, n_steps+1] int64 or None
     stat_sum_e2: object = None
     accept_hist: object = None        # [n_chains, n_bins] uint32 or None
-    n_near_threshold: object = None   # replay only
+    stat_count: object = None         # [n_groups, n_steps+1] int32: chains of the group with an energy at that index
+    n_near_threshold: object = None   # replay: |u - p| < 1e-6; production: decisions taken with the float64 rule (band hits)
+    n_fp32_flips: object = None       # production: band decisions float32 alone would have got wrong
     kernel_ms: float = 0.0
     gpu_launches: int = 0
     record: object = None             # [8, n_chains] int32: what a later segment needs besides the states
@@ -89,11 +91,16 @@ class RunResult:
 
     def save_checkpoint(self, path):
         """Everything needed to continue these chains later (``Engine.run(..., resume=load_checkpoint(path))``
-        with the same seeds and schedule): states, best states, the per-chain record and the step reached."""
+        with the same seeds and schedule): states, best states, the per-chain record, the step reached, and the
+        cumulative outputs a later segment continues into (statistics, acceptance bins) when the run has them.
+        Full histories and accept bitmaps are not saved: a resumed run that asks for them gets the columns of
+        the earlier segments as zeros."""
         def host(x):
             return np.asarray(x.cpu() if hasattr(x, "cpu") else x)
+        extra = {k: host(getattr(self, k)) for k in _CUMULATIVE if getattr(self, k) is not None}
         np.savez_compressed(path, record=host(self.record), final_state=host(self.final_state), best_state=host(self.best_state),
-                            meta=np.array([self.mode, self.n, self.q, self.n_steps, self.n_chains, self.step], dtype=np.int64))
+                            meta=np.array([self.mode, self.n, self.q, self.n_steps, self.n_chains, self.step], dtype=np.int64),
+                            **extra)
 
     def accepted_mask(self, chain):
         """bool[n_steps]: step s of ``chain`` was accepted (needs accept_bits)."""
@@ -102,12 +109,21 @@ class RunResult:
         return bits[: self.n_steps].astype(bool)
 
 
+#: outputs a later segment adds to (saved in checkpoints; allocated ZEROED when a resumed run has to create them)
+_CUMULATIVE = ("stat_sum_e", "stat_sum_e2", "stat_count", "accept_hist")
+_CONTINUED = _CUMULATIVE + ("energy_history", "accept_bits")
+
+
 def load_checkpoint(path):
     """RunResult holding the resumable part of a run written by ``RunResult.save_checkpoint``."""
     z = np.load(path)
     mode, n, q, ns, nc, step = (int(v) for v in z["meta"])
-    return RunResult(mode=mode, n=n, q=q, n_steps=ns, n_chains=nc, record=z["record"], final_state=z["final_state"],
-                     best_state=z["best_state"], step=step)
+    res = RunResult(mode=mode, n=n, q=q, n_steps=ns, n_chains=nc, record=z["record"], final_state=z["final_state"],
+                    best_state=z["best_state"], step=step)
+    for k in _CUMULATIVE:
+        if k in z.files:
+            setattr(res, k, z[k])
+    return res
 
 
 def _ptr(x):
@@ -197,16 +213,39 @@ class Engine:
                                               mv.ctypes.data, out.ctypes.data, _lib.MEM_HOST, None))
         return out
 
+    # ------------------------------------------------------------------ schedules, generator
+    def beta_table(self, schedules, n_steps):
+        """(beta float64 [n_groups, n_steps], c float32 [n_groups, n_steps]) of parametrised schedules as the DEVICE
+        evaluates them: the beta of the float64 accept rule and the -beta*log2(e) of the float32 fast path."""
+        plist = [schedules] if isinstance(schedules, dict) else list(schedules)
+        arr = _sched.device_schedules(plist)
+        beta = np.empty((len(plist), int(n_steps)), dtype=np.float64)
+        c = np.empty((len(plist), int(n_steps)), dtype=np.float32)
+        _lib.check(self._lib.mcq_beta_table(self._h, len(plist), C.addressof(arr), int(n_steps), beta.ctypes.data, c.ctypes.data))
+        return beta, c
+
+    def philox_device(self, counters, keys):
+        """Philox4x32-10 as compiled for the GPU: counters [n, 4], keys [n, 2] -> words [n, 4] (known-answer tests)."""
+        ctr = np.ascontiguousarray(counters, dtype=np.uint32).reshape(-1, 4)
+        key = np.ascontiguousarray(keys, dtype=np.uint32).reshape(-1, 2)
+        out = np.empty_like(ctr)
+        _lib.check(self._lib.mcq_philox4x32_10_device(self._h, ctr.shape[0], ctr.ctypes.data, key.ctypes.data, out.ctypes.data))
+        return out
+
     # ------------------------------------------------------------------ chains
-    def run(self, mcmc_type, n, n_steps, seeds, betas=None, *, q=None, groups=None, init_mode="random",
+    def run(self, mcmc_type, n, n_steps, seeds, betas=None, *, schedules=None, q=None, groups=None, init_mode="random",
             init_states=None, history="full", hist_dtype=None, accept_bits=False, n_bins=0,
             early_stop_patience=None, replay=None, want_states=True, device_buffers=False,
-            beta_device_table=None, lanes_per_chain=0, warps_per_cta=0, chunk_steps=0, max_chains_per_sm=0,
-            algo=0, stream=None, out=None, stop_step=None, resume=None) -> RunResult:
+            lanes_per_chain=0, warps_per_cta=0, chunk_steps=0, max_chains_per_sm=0,
+            algo=0, stream=None, out=None, stop_step=None, resume=None, stat_count=False,
+            accept_all_f64=False) -> RunResult:
         """Run ``len(seeds)`` independent chains.
 
-        seeds   uint64 per chain (the Philox key; reference: ``base_seed + r``, experiments.py:508)
-        betas   float64 [n_groups, n_steps] (or [n_steps]) table of beta(step); chain c uses row groups[c]
+        seeds   uint64 per chain (the chain's random stream; reference: ``base_seed + r``, experiments.py:508)
+        schedules  one ``schedule_params`` dict per group (or a single dict): beta(step) is evaluated on the
+                device from the parameters (experiments.py:13-77); chain c uses schedule groups[c]
+        betas   instead of ``schedules``: float64 [n_groups, n_steps] (or [n_steps]) table of beta(step) -- an
+                arbitrary closure tabulated by the caller, and the exact betas of a replay
         history "full" (per-chain energies), "stats" (per-group sum E / sum E^2 only) or "none"
         replay  dict(moves=[n_chains,n_steps,3|4], uniforms=[n_chains,n_steps]) to consume a recorded
                 stream instead of Philox (float64 accept test; betas must be the exact float64 table)
@@ -234,36 +273,44 @@ class Engine:
             if resume.record is None or resume.final_state is None or resume.best_state is None:
                 raise ValueError("resume needs a result with record, final_state and best_state (want_states=True)")
             start, init_states = int(resume.step), resume.final_state
-            for name in ("energy_history", "accept_bits", "accept_hist", "stat_sum_e", "stat_sum_e2"):
+            for name in _CONTINUED:
                 if getattr(resume, name, None) is not None:
                     out.setdefault(name, getattr(resume, name))
         p = _lib.RunParams()
         p.struct_size = C.sizeof(_lib.RunParams)
         p.mode, p.n, p.q, p.n_steps, p.n_chains = mode, n, q, ns, nc
         p.mem = _lib.MEM_DEVICE if device_buffers else _lib.MEM_HOST
+        if device_buffers and stream is None:
+            # torch allocates, fills and copies on ITS current stream; run libmcq on the same one so that
+            # inputs are staged before the kernels read them and zero-fills land before the kernels write
+            import torch
+            stream = torch.cuda.current_stream(self.device).cuda_stream
         p.early_stop_patience = -1 if early_stop_patience is None else int(early_stop_patience)
         keep = [seeds_in]
         p.chain_seeds = _ptr(seeds_in)
 
-        # schedules
-        if beta_device_table is not None:      # caller-resident float32 table (bench: inputs in HBM)
-            tab = beta_device_table
-            n_groups = 1 if tab.ndim == 1 else int(tab.shape[0])
-            p.beta_log2e = _ptr(tab)
-            keep.append(tab)
+        # schedules: parameters (evaluated on the device) or a float64 table (closures, replays)
+        if schedules is not None:
+            if replay is not None:
+                raise ValueError("a replay needs the exact float64 `betas` table, not `schedules`")
+            plist = [schedules] if isinstance(schedules, dict) else list(schedules)
+            arr = _sched.device_schedules(plist)
+            n_groups = len(plist)
+            p.schedules = C.addressof(arr)
+            keep.append(arr)
         else:
-            b = np.asarray(betas, dtype=np.float64)
+            if betas is None:
+                raise ValueError("give `schedules` (parameters) or `betas` (a float64 table)")
+            b = betas
+            if not (device_buffers and hasattr(b, "data_ptr")):
+                b = np.asarray(b, dtype=np.float64)
             if b.ndim == 1:
                 b = b[None, :]
             if b.shape[1] != ns:
                 raise ValueError(f"beta table has {b.shape[1]} steps, expected {ns}")
             n_groups = int(b.shape[0])
-            if replay is None:
-                tab = self._in(_sched.to_device_table(b), np.float32, device_buffers)
-                p.beta_log2e = _ptr(tab)
-            else:
-                tab = self._in(b, np.float64, device_buffers)
-                p.beta_f64 = _ptr(tab)
+            tab = self._in(b, np.float64, device_buffers)
+            p.beta_f64 = _ptr(tab)
             keep.append(tab)
         p.n_groups = n_groups
         if groups is not None:
@@ -297,7 +344,13 @@ class Engine:
         def buf(name, shape, dtype, zero=False):
             a = out.get(name)
             if a is None:
-                a = self._alloc(shape, dtype, device_buffers, zero)
+                # a resumed segment continues into these arrays: what earlier segments would have left there
+                # must at least be defined (zeros) when the caller does not hand their arrays back
+                a = self._alloc(shape, dtype, device_buffers, zero or (resume is not None and name in _CONTINUED))
+            elif not device_buffers and not isinstance(a, np.ndarray):
+                a = np.ascontiguousarray(a.cpu() if hasattr(a, "cpu") else a, dtype=dtype)
+            elif device_buffers and isinstance(a, np.ndarray):
+                a = self._in(a, dtype, True)
             setattr(res, name, a)
             return _ptr(a)
 
@@ -309,6 +362,8 @@ class Engine:
         elif history == "stats":
             p.stat_sum_e = buf("stat_sum_e", (n_groups, ns + 1), np.int64)
             p.stat_sum_e2 = buf("stat_sum_e2", (n_groups, ns + 1), np.int64)
+            if stat_count or early_stop_patience is not None:
+                p.stat_count = buf("stat_count", (n_groups, ns + 1), np.int32)
         if accept_bits:
             p.accept_bits = buf("accept_bits", (nc, max(1, (ns + 31) // 32)), np.uint32, zero=True)
         if n_bins:
@@ -325,8 +380,10 @@ class Engine:
         if want_states:
             p.final_state = buf("final_state", (nc,) + sshape, np.uint8)
             p.best_state = buf("best_state", (nc,) + sshape, np.uint8)
-        if replay is not None:
-            p.n_near_threshold = buf("n_near_threshold", (nc,), np.uint32)
+        p.n_near_threshold = buf("n_near_threshold", (nc,), np.uint32)
+        if replay is None:
+            p.n_fp32_flips = buf("n_fp32_flips", (nc,), np.uint32)
+        p.accept_all_f64 = int(bool(accept_all_f64))
         ms, launches = C.c_float(0.0), C.c_int32(0)
         p.kernel_ms = C.addressof(ms)
         p.gpu_launches = C.addressof(launches)

@@ -141,5 +141,46 @@ def tabulate(beta_schedule=None, schedule_params=None, n_steps=0):
 
 
 def to_device_table(betas):
-    """float32 ``-beta * log2(e)``: accept test is ``u < 2**(c_t * dE)``."""
+    """float32 ``-beta * log2(e)``: what the float32 fast path of the accept test reads (the engine builds
+    this table on the device, csrc/accept.cuh: beta_table_kernel; this host copy is for tests)."""
     return np.ascontiguousarray((-np.asarray(betas, dtype=np.float64)) * LOG2E, dtype=np.float32)
+
+
+_TYPE_IDS = {name: i for i, name in enumerate(SCHEDULE_TYPES)}
+
+
+def describe(beta_schedule=None, schedule_params=None, n_steps=None):
+    """The ``schedule_params`` dict of a schedule the device can evaluate itself, or ``None`` when only a
+    step-by-step tabulation will do (an arbitrary callable, e.g. one built by the reference's own factories).
+    Same precedence and the same errors as :func:`tabulate`."""
+    if schedule_params is not None:
+        params = dict(schedule_params)
+    else:
+        if beta_schedule is None:
+            raise ValueError("a beta schedule is required")
+        tag = getattr(beta_schedule, "params", None)
+        if tag is None or getattr(beta_schedule, "n_steps", None) not in (None, n_steps):
+            return None
+        params = dict(tag)
+    kind = params.get("type")
+    if kind == "constant":
+        if params.get("beta_const") is None:
+            raise ValueError("beta_const required for constant schedule")
+    elif kind not in SCHEDULE_TYPES:
+        raise ValueError(f"Unknown betta_scheduling type: {kind}")
+    elif params.get("beta_start") is None or params.get("beta_end") is None:
+        raise ValueError(f"beta_start and beta_end required for {kind} schedule")
+    return params
+
+
+def device_schedules(param_list):
+    """ctypes array of ``mcq_schedule`` (include/mcq.h) for a list of ``schedule_params`` dicts."""
+    from . import _lib
+    arr = (_lib.Schedule * len(param_list))()
+    for i, p in enumerate(param_list):
+        p = describe(schedule_params=p)
+        arr[i].type = _TYPE_IDS[p["type"]]
+        arr[i].beta_const = float(p.get("beta_const") or 0.0)
+        arr[i].beta_start = float(p.get("beta_start") or 0.0)
+        arr[i].beta_end = float(p.get("beta_end") or 0.0)
+    return arr

@@ -22,13 +22,11 @@ LIN = {"type": "linear_annealing", "beta_start": 1.0, "beta_end": 3.0}
 
 def run(tag, mode, n, nc, ns, history="none", **kw):
     import torch
-    betas = schedules.beta_table(LIN, ns)
-    tab = torch.from_numpy(schedules.to_device_table(betas)).cuda()
     seeds = torch.arange(nc, dtype=torch.int64).cuda()
     best = None
     for _ in range(2):
         t0 = time.time()
-        r = eng.run(mode, n, ns, seeds, None, beta_device_table=tab, history=history, device_buffers=True,
+        r = eng.run(mode, n, ns, seeds, schedules=LIN, history=history, device_buffers=True,
                     want_states=False, **kw)
         wall = time.time() - t0
         pps = nc * ns / (r.kernel_ms * 1e-3)

@@ -92,7 +92,7 @@ def test_c_abi_exports_every_declared_symbol():
         getattr(lib, name)
     assert declared == {name for name, _, _ in _lib.SYMBOLS}
     lib = _lib.load()
-    assert lib.mcq_abi_version() == 2
+    assert lib.mcq_abi_version() == 3
     assert lib.mcq_sizeof_run_params() == C.sizeof(_lib.RunParams)
     # every field of the ctypes mirror appears in the header struct, in order
     body = header[header.index("typedef struct mcq_run_params {"): header.index("} mcq_run_params;")]

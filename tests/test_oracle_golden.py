@@ -137,3 +137,84 @@ def test_c_generator_is_self_consistent():
                     h[a] = (b, c, d)
             cur += delta if acc else 0
             assert cur == g["history"][step + 1]
+
+
+# ---- the Philox-driven statement of the production chain (oracle/c/queens_philox.c) ----
+def test_oracle_philox_known_answers():
+    """The C oracle's own Philox4x32-10 against the Random123 known-answer vectors."""
+    from oracle import c_oracle as co
+    assert co.philox((0, 0, 0, 0), (0, 0)) == (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)
+    assert co.philox((0xffffffff,) * 4, (0xffffffff,) * 2) == (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)
+    assert co.philox((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0)) == \
+        (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1)
+
+
+@pytest.mark.parametrize("mode", ["board", "full_3d"])
+@pytest.mark.parametrize("n,patience", [(4, None), (8, None), (12, None), (12, 300), (7, 0)])
+def test_philox_chain_is_the_reference_loop_on_its_recorded_stream(mode, n, patience):
+    """The production-chain oracle records the proposals and uniforms it draws; the replay oracle (pinned to the
+    reference by the golden fixtures above) fed with that stream must reproduce every output.  So the only thing
+    the Philox oracle adds to reference-pinned logic is the documented word -> proposal mapping."""
+    from oracle import c_oracle as co
+    ns = 4000
+    betas = np.array([1.0 + (s / (ns - 1)) * 2.0 for s in range(ns)])
+    pat = patience if mode == "board" else None
+    r = co.philox_chain(mode, n, 1234 + n, betas, patience=pat, record=True)
+    done = r["steps_done"]
+    moves = r["moves"][:, :3] if mode == "board" else r["moves"]
+    rr = co.replay(mode, n, r["init_state"], moves, r["uniforms"], betas, patience=pat)
+    for k in ("history", "accepted", "final_state", "best_state"):
+        assert np.array_equal(r[k], rr[k]), k
+    for k in ("best_energy", "final_energy", "steps_to_best", "steps_done"):
+        assert r[k] == rr[k], k
+    assert done == ns or patience is not None
+    # legality of the drawn proposals: board never proposes the current height, full_3d never an occupied cell
+    # (replay() raises on an illegal move), and the uniforms are 53-bit fractions in [0, 1)
+    u = r["uniforms"][: min(done + 1, ns)]
+    assert (u >= 0).all() and (u < 1).all() and (np.round(u * 2.0 ** 53) == u * 2.0 ** 53).all()
+
+
+@pytest.mark.parametrize("mode", ["board", "full_3d"])
+def test_philox_proposals_are_uniform(mode):
+    """Distribution of the drawn proposals (experiments.py:221-231, :311-319): uniform queen / column, uniform
+    over the other heights / the empty cells -- chi-square on a constant-state chain (beta so large nothing
+    uphill is accepted would still move; use recorded moves of many short chains from the same start)."""
+    from oracle import c_oracle as co
+    n = 5
+    counts = {}
+    betas = np.full(1, 50.0)
+    state = co.philox_init_state(mode, n, "latin", 0)
+    for seed in range(6000):
+        r = co.philox_chain(mode, n, seed, betas, state=state, record=True)
+        key = tuple(int(v) for v in r["moves"][0])
+        counts[key] = counts.get(key, 0) + 1
+    total = sum(counts.values())
+    if mode == "board":
+        n_out = n * n * (n - 1)
+        assert all(state[i, j] != k for (i, j, k, _z) in counts)          # never the current height
+    else:
+        occ = {tuple(c) for c in state.tolist()}
+        n_out = n * n * (n ** 3 - n * n)
+        assert all((i, j, k) not in occ for (_q, i, j, k) in counts)      # never an occupied cell
+    exp = total / n_out
+    chi2 = sum((c - exp) ** 2 / exp for c in counts.values()) + (n_out - len(counts)) * exp
+    # chi-square with n_out - 1 degrees of freedom: mean n_out, sd sqrt(2 n_out)
+    assert abs(chi2 - n_out) < 5 * (2 * n_out) ** 0.5
+
+
+@pytest.mark.parametrize("mode,n,init_mode", [("board", 12, "klarner"), ("full_3d", 12, "klarner"), ("board", 11, "klarner"),
+                                              ("full_3d", 8, "latin"), ("board", 6, "random"), ("full_3d", 6, "random")])
+def test_philox_init_states_are_legal_and_structured(mode, n, init_mode):
+    from oracle import c_oracle as co
+    from oracle import queens_numpy as qn
+    st = co.philox_init_state(mode, n, init_mode, 99)
+    if mode == "board":
+        assert st.shape == (n, n) and st.min() >= 0 and st.max() < n
+        if init_mode == "klarner":
+            m = n if np.gcd(n, 210) == 1 else max(k for k in range(1, n) if np.gcd(k, 210) == 1)
+            i, j = np.indices((m, m))
+            assert (st[:m, :m] == (3 * i + 5 * j) % m).all()                # mcmc_board.py:34-36, :50-52
+    else:
+        assert st.shape == (n * n, 3) and len({tuple(c) for c in st.tolist()}) == n * n
+        if init_mode == "latin":
+            assert (st == qn.init_full(n, "latin")).all()
