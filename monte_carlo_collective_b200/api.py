@@ -19,7 +19,7 @@ import time
 import numpy as np
 
 from . import schedules as _sched
-from .engine import BOARD, FULL, default_engine
+from .engine import BOARD, FULL
 from .states import State3DQueens, State3DQueensBoard
 
 build_schedule_from_params = _sched.build_schedule_from_params
@@ -52,39 +52,105 @@ def _verbose_trace(history, n_steps, best_energy):
     print(int(best_energy))
 
 
+class StepIndices:
+    """``accepted_steps`` / ``rejected_steps`` of one chain (experiments.py:329-332) without the list.
+
+    The reference appends every step index to one of two Python lists: 16 bytes per proposal as NumPy int64,
+    several times that as a list.  The engine keeps one BIT per proposal; this sequence is a view of a chain's
+    bitmap row that behaves like the list for its consumers (``len``, iteration, indexing, ``list.extend``,
+    ``np.array`` / ``np.concatenate`` -- plot_acceptance_rates_binned, experiments.py:669-686) and materialises
+    the int64 indices only when asked."""
+
+    __slots__ = ("_words", "_ran", "_accepted", "_cache")
+
+    def __init__(self, words, ran, accepted):
+        self._words, self._ran, self._accepted, self._cache = words, int(ran), bool(accepted), None
+
+    def mask(self):
+        """bool[ran]: membership of steps 0..ran-1."""
+        bits = np.unpackbits(np.ascontiguousarray(self._words).view(np.uint8), bitorder="little")[: self._ran].astype(bool)
+        return bits if self._accepted else ~bits
+
+    def __len__(self):
+        if self._cache is not None:
+            return len(self._cache)
+        full, rem = divmod(self._ran, 32)
+        w = np.ascontiguousarray(self._words[: full + (1 if rem else 0)]).copy()
+        if rem:
+            w[-1] &= np.uint32((1 << rem) - 1)
+        n_acc = int(np.unpackbits(w.view(np.uint8)).sum())
+        return n_acc if self._accepted else self._ran - n_acc
+
+    def __array__(self, dtype=None, copy=None):
+        if self._cache is None:
+            self._cache = np.flatnonzero(self.mask())
+        return self._cache if dtype is None else self._cache.astype(dtype)
+
+    def __iter__(self):
+        return iter(self.__array__().tolist())
+
+    def __getitem__(self, k):
+        return self.__array__()[k]
+
+    def __eq__(self, other):
+        return np.array_equal(self.__array__(), np.asarray(other))
+
+    def tolist(self):
+        return self.__array__().tolist()
+
+    def __repr__(self):
+        return f"StepIndices({'accepted' if self._accepted else 'rejected'}, n={len(self)}, of {self._ran} steps)"
+
+
+def _step_lists(res, c):
+    done = int(res.steps_done[c])
+    ran = min(done + 1, res.n_steps)                       # an early-stopped step still logs accept/reject
+    if getattr(res, "accept_bits", None) is not None:
+        words = res.accept_bits[c]
+        return StepIndices(words, ran, True), StepIndices(words, ran, False)
+    mask = res.accepted_mask(c)[:ran]                      # (result objects without a bitmap: test doubles)
+    steps = np.arange(ran)
+    return steps[mask], steps[~mask]
+
+
 def _chain_dict(mode, n, res, c):
     """Per-chain return value of metropolis_mcmc* (experiments.py:270-279, :367-376)."""
     done = int(res.steps_done[c])
-    hist = res.energy_history[c, : done + 1]
-    mask = res.accepted_mask(c)
-    ran = min(done + 1, res.n_steps)                       # an early-stopped step still logs accept/reject
-    steps = np.arange(ran)
+    acc, rej = _step_lists(res, c)
     return {
         "final_state": _make_state(mode, n, res.final_state[c], res.final_energy[c]),
         "final_energy": int(res.final_energy[c]),
         "best_state": _make_state(mode, n, res.best_state[c], res.best_energy[c]),
         "best_energy": int(res.best_energy[c]),
-        "energy_history": hist,
-        "accepted_steps": steps[mask[:ran]],
-        "rejected_steps": steps[~mask[:ran]],
+        "energy_history": res.energy_history[c, : done + 1],   # a view of the batch's history array
+        "accepted_steps": acc,
+        "rejected_steps": rej,
         "steps_to_best": int(res.steps_to_best[c]),
     }
 
 
-def _run_batch(mode, N, n_steps, init_mode, betas, seeds, Q=None, early_stop_patience=None):
+def _run_batch(mode, N, n_steps, init_mode, schedule, seeds, Q=None, early_stop_patience=None, want_states=True):
+    """One batch of chains on every visible GPU (multi.DevicePool).  ``schedule``: a ``schedule_params`` dict
+    (evaluated on the device) or a float64 table of beta(step) (a closure tabulated on the host)."""
+    from .multi import default_pool
     if early_stop_patience in _NONE_STRINGS:
         early_stop_patience = None
-    eng = default_engine()
-    return eng.run(mode, N, n_steps, np.asarray(seeds, dtype=np.uint64), betas, q=Q, init_mode=init_mode,
-                   history="full", accept_bits=True,
-                   early_stop_patience=early_stop_patience if mode == BOARD else None)
+    kw = dict(schedules=schedule) if isinstance(schedule, dict) else dict(betas=schedule)
+    return default_pool().run(mode, N, n_steps, np.asarray(seeds, dtype=np.uint64), q=Q, init_mode=init_mode,
+                              history="full", accept_bits=True, want_states=want_states,
+                              early_stop_patience=early_stop_patience if mode == BOARD else None, **kw)
+
+
+def _schedule_of(beta_schedule, schedule_params, n_steps):
+    """Parameters when the device can evaluate the schedule itself, else its float64 table."""
+    params = _sched.describe(beta_schedule, schedule_params, n_steps)
+    return params if params is not None else _sched.tabulate(beta_schedule, None, n_steps)
 
 
 def metropolis_mcmc(N, n_steps, init_mode, beta_schedule, verbose=True, seed=None, Q=None, run_idx=None,
                     early_stop_patience=None):
     """full_3d chain, experiments.py:199-279 (``early_stop_patience`` is ignored there as well)."""
-    betas = _sched.tabulate(beta_schedule, None, n_steps)
-    res = _run_batch(FULL, N, n_steps, init_mode, betas, [_seed_value(seed)], Q=Q)
+    res = _run_batch(FULL, N, n_steps, init_mode, _schedule_of(beta_schedule, None, n_steps), [_seed_value(seed)], Q=Q)
     out = _chain_dict(FULL, N, res, 0)
     out["energy_history"] = out["energy_history"].tolist()
     out["accepted_steps"] = out["accepted_steps"].tolist()
@@ -97,8 +163,8 @@ def metropolis_mcmc(N, n_steps, init_mode, beta_schedule, verbose=True, seed=Non
 def metropolis_mcmc_board(N, n_steps, init_mode, beta_schedule, verbose=True, seed=None, run_idx=None,
                           early_stop_patience=None):
     """Board-constrained chain, experiments.py:282-376."""
-    betas = _sched.tabulate(beta_schedule, None, n_steps)
-    res = _run_batch(BOARD, N, n_steps, init_mode, betas, [_seed_value(seed)], early_stop_patience=early_stop_patience)
+    res = _run_batch(BOARD, N, n_steps, init_mode, _schedule_of(beta_schedule, None, n_steps), [_seed_value(seed)],
+                     early_stop_patience=early_stop_patience)
     out = _chain_dict(BOARD, N, res, 0)
     out["energy_history"] = out["energy_history"].tolist()
     out["accepted_steps"] = out["accepted_steps"].tolist()
@@ -161,24 +227,29 @@ def run_experiment(N, n_steps, init_mode, beta_schedule, n_runs, base_seed=0, ve
         return [], [], [], [], [], []
     # the sequential branch of the reference (n_runs == 1, :548-558) does not forward the patience
     patience = early_stop_patience if n_runs > 1 else None
-    betas = _sched.tabulate(beta_schedule, schedule_params if n_runs > 1 else None, n_steps)
+    schedule = _schedule_of(beta_schedule, schedule_params if n_runs > 1 else None, n_steps)
     seeds = [base_seed + r for r in range(n_runs)]
     t0 = time.time()
-    res = _run_batch(mode, N, n_steps, init_mode, betas, seeds, early_stop_patience=patience)
+    res = _run_batch(mode, N, n_steps, init_mode, schedule, seeds, early_stop_patience=patience, want_states=False)
     elapsed = time.time() - t0
 
+    # what the reference returns as Python lists of n_steps ints per chain comes back as views: rows of the batch's
+    # history array (uint16 / int32) and bitmap-backed step lists -- no per-chain copies, so a batch of thousands
+    # of million-step chains stays within the bytes the device produced
     histories, best, times, acc, rej, s2b = [], [], [], [], [], []
     for r in range(n_runs):
-        d = _chain_dict(mode, N, res, r)
-        histories.append(d["energy_history"])
-        best.append(d["best_energy"])
+        done = int(res.steps_done[r])
+        hist = res.energy_history[r, : done + 1]
+        a_steps, r_steps = _step_lists(res, r)
+        histories.append(hist)
+        best.append(int(res.best_energy[r]))
         times.append(elapsed)
-        acc.append(d["accepted_steps"])
-        rej.append(d["rejected_steps"])
-        s2b.append(d["steps_to_best"])
+        acc.append(a_steps)
+        rej.append(r_steps)
+        s2b.append(int(res.steps_to_best[r]))
         if verbose:
-            _verbose_trace(d["energy_history"], n_steps, d["best_energy"])
-            print(d["best_energy"])
+            _verbose_trace(hist, n_steps, best[-1])
+            print(best[-1])
     return histories, best, times, acc, rej, s2b
 
 

@@ -597,7 +597,7 @@ int mcq_chain_smem_bytes(int mode, int n, int q, int lanes_per_chain) {
 
 int mcq_host_alloc(void **ptr, uint64_t bytes) {
     if (!ptr) return fail(MCQ_EINVAL, "ptr is NULL");
-    CUDA_TRY(cudaHostAlloc(ptr, (size_t)bytes, cudaHostAllocDefault));
+    CUDA_TRY(cudaHostAlloc(ptr, (size_t)bytes, cudaHostAllocPortable));   // usable from every device of the box
     return 0;
 }
 

@@ -37,10 +37,13 @@ class FakeResult:
         return self._acc[c]
 
 
-def fake_run_batch(mode, N, n_steps, init_mode, betas, seeds, Q=None, early_stop_patience=None):
+def fake_run_batch(mode, N, n_steps, init_mode, schedule, seeds, Q=None, early_stop_patience=None, want_states=True):
     if early_stop_patience in (None, "None", "null"):
         early_stop_patience = None
-    table = np.asarray(betas).reshape(-1)
+    if isinstance(schedule, dict):
+        from monte_carlo_collective_b200 import schedules
+        schedule = schedules.beta_table(schedule, n_steps)
+    table = np.asarray(schedule).reshape(-1)
     chains = [qn.run_chain(mode, N, n_steps, init_mode, lambda s: table[s], seed=int(sd),
                            early_stop_patience=early_stop_patience if mode == "board" else None) for sd in seeds]
     return FakeResult(mode, N, n_steps, chains)
