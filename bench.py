@@ -1,25 +1,28 @@
 #!/usr/bin/env python
-"""Headline benchmark: MCMC proposals/sec on BASELINE config C2.
+"""Headline benchmark: MCMC proposals/sec on the BASELINE configs.
 
-Workload (BASELINE.json configs[1]): 3D N^2-queens, N=12, full_3d state
-space, random initial states, the five beta schedules {constant 5.0; linear, exponential,
-logarithmic, sinusoidal 1.0->3.0}, 4096 replicas per schedule (20480 chains) per GPU,
-n_steps = 1e6 proposals per chain.  One bench "step" = one pass of that batch through the hot
-path (2.048e10 proposals per GPU), producing what the experiment consumes: per-schedule
-sum E / sum E^2 per step (mean +- std curves), per-chain best / final energy, steps-to-best,
-accept counts, 100-bin acceptance histograms and best / final states.
+Default workload (BASELINE.json configs[1]) -- `--workload c2`: 3D N^2-queens, N=12,
+full_3d state space, random initial states, the five beta schedules {constant 5.0; linear, exponential,
+logarithmic, sinusoidal 1.0->3.0}, 4096 replicas per schedule (20480 chains) per GPU, n_steps = 1e6 proposals
+per chain.  One bench "step" = one pass of that batch through the hot path (2.048e10 proposals per GPU),
+producing what the experiment consumes: per-schedule sum E / sum E^2 per step (mean +- std curves), per-chain
+best / final energy, steps-to-best, accept counts, 100-bin acceptance histograms and best / final states.
+`--workload c4` (N=20 board, exponential, 64 (beta_start, beta_end) pairs x 1024 replicas) and `--workload c5`
+(N=64 board, 65536 replicas, linear 1->3) time the other single-launch configs with the same line shape.
 
-  value  proposals/s with inputs (seeds, schedule tables, group ids) resident in HBM and outputs
-         left in HBM (MCQ_MEM_DEVICE), timed with CUDA events on the launching stream.
-  e2e    the same pass through the public host-buffer API (Engine.run -> mcq_run, MCQ_MEM_HOST):
-         pinned host inputs are copied H2D and every result is copied D2H inside the timed region.
-  N>1    one process per GPU (torchrun); replicas are sharded (each GPU runs its own 4096
-         replicas per schedule: weak scaling), no data-path collective; the per-schedule
-         statistics and the global best energy are reduced once with NCCL inside the timed step.
+  value    proposals/s with inputs (seeds, group ids, schedule parameters) resident in HBM and outputs left in
+           HBM (MCQ_MEM_DEVICE), timed with CUDA events on the launching stream.
+  e2e      the same pass through the public host-buffer API (Engine.run -> mcq_run, MCQ_MEM_HOST): host inputs are
+           copied H2D and every result is copied D2H inside the timed region.
+  e2e_api  (N=1, c2) the reference's own call, run_experiment(N=12, n_runs=4096, n_steps=1e6, mcmc_type="full_3d"),
+           through the drop-in API: full uint16 histories and accept bitmaps of every chain come back to the host.
+  N>1      one process per GPU (torchrun); replicas are sharded (each GPU runs its own replicas: weak scaling), no
+           data-path collective; per-schedule statistics and the global best energy are reduced with NCCL inside
+           the timed step, segment by segment under the kernels of the next segment.
 
-`--impl reference` times the reference's CPU algorithm (oracle/queens_numpy.py, a line-by-line
-NumPy restatement pinned to the reference by tests/golden; the reference itself is pure Python and
-does not exist on the GPU box) on all host cores, same workload definition, bounded sample.
+`--impl reference` times the reference's CPU algorithm (oracle/queens_numpy.py, a NumPy restatement pinned to the
+reference by tests/golden; the reference itself is pure Python and does not exist on the GPU box) on all host
+cores, same workload definition, bounded sample.
 """
 from __future__ import annotations
 
@@ -37,27 +40,32 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-N_BOARD = 12
-REPLICAS = 4096
-CHAIN_STEPS = 1_000_000
 BASE_SEED = 42
-SCHEDULES = [
+C2_SCHEDULES = [
     {"type": "constant", "beta_const": 5.0},
     {"type": "linear_annealing", "beta_start": 1.0, "beta_end": 3.0},
     {"type": "exponential_annealing", "beta_start": 1.0, "beta_end": 3.0},
     {"type": "logarithmic_annealing", "beta_start": 1.0, "beta_end": 3.0},
     {"type": "sinusoidal_annealing", "beta_start": 1.0, "beta_end": 3.0},
 ]
+C4_STARTS = (0.1, 0.25, 0.5, 0.75, 1.0, 1.5, 2.0, 3.0)
+C4_ENDS = (2.0, 3.0, 4.0, 5.0, 6.0, 8.0, 10.0, 20.0)
+WORKLOADS = {
+    "c2": dict(n=12, mode="full_3d", replicas=4096, chain_steps=1_000_000, schedules=C2_SCHEDULES,
+               name="C2 single_N: N=12 full_3d, 5 beta schedules x %d replicas per GPU, %d proposals per chain, random init"),
+    "c4": dict(n=20, mode="board", replicas=1024, chain_steps=1_000_000,
+               schedules=[{"type": "exponential_annealing", "beta_start": a, "beta_end": b} for a in C4_STARTS for b in C4_ENDS],
+               name="C4 beta_start_end_pairs: N=20 board, exponential, 64 (beta_start, beta_end) pairs x %d replicas per GPU, %d proposals per chain"),
+    "c5": dict(n=64, mode="board", replicas=65536, chain_steps=1_000_000,
+               schedules=[{"type": "linear_annealing", "beta_start": 1.0, "beta_end": 3.0}],
+               name="C5 scaling stress: N=64 board (4096 queens), linear 1->3, %d replicas per GPU, %d proposals per chain"),
+}
 # algorithmic warp-instructions per proposal, one warp per chain
-I_ALG = {"full_3d": 48.0, "board": 40.0}
+I_ALG_SURVEY = {"full_3d": 48.0, "board": 40.0}
 ISSUE_PER_CLK_PER_SM = 4
-# ncu measurements of the dominant kernel on this workload (profiles/README.md says which capture)
-AS_BUILT = {"source": "profiles/r1_spec_kernel_raw.txt (ncu --set full, chunk launch of 20480 chains x 26208 steps)",
-            "warp_inst_per_proposal": 9.8, "issue_active_pct": 65.0, "warps_active_per_scheduler": 6.3,
-            "registers_per_thread": 72, "smem_wavefronts_per_proposal": 2.60, "smem_wavefront_pct_of_peak": 66.2,
-            "speculated_steps_per_round": 32, "proposals_retired_per_round": 19.4, "cycles_per_round_per_warp": 1950,
-            "dram_bytes_per_launch": 1.057e9, "algorithmic_bytes_per_launch": 1.073e9}
-
+# ncu measurements of the dominant kernel on the c2 workload live in profiles/r2_as_built.json (a LABELLED copy of
+# this round's capture: the run itself measures time, acceptance and clocks, not hardware counters)
+AS_BUILT_FILE = os.path.join(ROOT, "profiles", "r2_as_built.json")
 
 _REAL_STDOUT = None
 
@@ -113,11 +121,14 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
-def chain_seeds(rank, replicas):
-    """Seed of replica r of any schedule on this rank: base_seed + global replica index (the
-    reference gives every schedule the same base_seed, experiments.py:157,194)."""
+def chain_seeds(key, rank, replicas):
+    """Seed of replica r of schedule group g on this rank.  c2: every schedule has the same base_seed
+    (experiments.py:157,194); c4: pair idx uses base_seed + idx*1000 + r (:791); ranks continue the replica index."""
     r = np.arange(replicas, dtype=np.uint64) + np.uint64(rank * replicas) + np.uint64(BASE_SEED)
-    return np.tile(r, len(SCHEDULES))
+    ng = len(WORKLOADS[key]["schedules"])
+    if key == "c4":
+        return np.concatenate([r + np.uint64(1000 * g) for g in range(ng)])
+    return np.tile(r, ng)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -125,22 +136,33 @@ def chain_seeds(rank, replicas):
 # ----------------------------------------------------------------------------------------------
 def _cpu_chain(args):
     from oracle import queens_numpy as qn
-    sched_idx, seed, steps = args
-    sched = qn.schedule_from_params(SCHEDULES[sched_idx], steps)
-    r = qn.chain_full(N_BOARD, steps, "random", sched, seed=seed)
+    key, sched_idx, seed, steps = args
+    wl = WORKLOADS[key]
+    sched = qn.schedule_from_params(wl["schedules"][sched_idx], steps)
+    if wl["mode"] == "full_3d":
+        r = qn.chain_full(wl["n"], steps, "random", sched, seed=seed)
+    else:
+        r = qn.chain_board(wl["n"], steps, "random", sched, seed=seed)
     return r["best_energy"]
 
 
-def cpu_pass(cores, steps):
+def cpu_pass(key, cores, steps):
     """One bounded sample: `cores` chains (schedules round-robin) x `steps` proposals, one process per core
     (what run_experiment does with its ProcessPoolExecutor, experiments.py:513)."""
     from concurrent.futures import ProcessPoolExecutor
-    jobs = [(c % len(SCHEDULES), BASE_SEED + c, steps) for c in range(cores)]
+    ng = len(WORKLOADS[key]["schedules"])
+    jobs = [(key, c % ng, BASE_SEED + c, steps) for c in range(cores)]
     t0 = time.perf_counter()
     with ProcessPoolExecutor(max_workers=cores) as ex:
         best = list(ex.map(_cpu_chain, jobs))
     dt = time.perf_counter() - t0
     return cores * steps / dt, dt, best
+
+
+CPU_KIND_NOTE = ("port: oracle/queens_numpy.py, a NumPy restatement of the reference chain (same algorithm, cost model and "
+                 "RNG call order; bit-identical trajectories, tests/golden).  The unmodified reference is pure Python and "
+                 "does not travel to the GPU box; on the authoring container the port is 1.35-1.4x FASTER per core than the "
+                 "reference itself (full_3d N=12: 9199 vs 6844 proposals/s), so ratios against it are conservative")
 
 
 def run_reference_arm(args, rank, world):
@@ -149,19 +171,19 @@ def run_reference_arm(args, rank, world):
     cores = len(os.sched_getaffinity(0))
     steps = args.cpu_steps
     for _ in range(args.warmup):
-        cpu_pass(cores, max(200, steps // 20))
-    rates, times = [], []
+        cpu_pass(args.workload, cores, max(200, steps // 20))
+    times = []
     for _ in range(args.steps):
-        pps, dt, _ = cpu_pass(cores, steps)
-        rates.append(pps)
+        _pps, dt, _ = cpu_pass(args.workload, cores, steps)
         times.append(dt)
     total = cores * steps * args.steps / sum(times)
-    sample = f"{cores} chains x {steps} proposals per step (schedules round-robin), N=12 full_3d random init"
+    wl = WORKLOADS[args.workload]
+    sample = f"{cores} chains x {steps} proposals per step (schedules round-robin), N={wl['n']} {wl['mode']} random init; {CPU_KIND_NOTE}"
     line = {
         "impl": "reference", "metric": "MCMC proposals/sec", "value": total, "unit": "proposals/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64+f64", "data": "synthetic",
-        "config": workload_config(args, 1, cpu=True),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64 energies, f64 accept (NumPy)", "data": "synthetic",
+        "config": workload_config(args, args.gpus),
         "cpu_baseline": {"value": total, "unit": "proposals/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": total, "unit": "proposals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -169,16 +191,23 @@ def run_reference_arm(args, rank, world):
     emit(line)
 
 
-def workload_config(args, world, cpu=False):
+def workload_config(args, world):
+    """Identical in both arms (the driver compares them)."""
+    wl = WORKLOADS[args.workload]
+    ng = len(wl["schedules"])
     return {
-        "workload": "C2 single_N: N=12 full_3d, 5 beta schedules x %d replicas per GPU, %d proposals per chain, random init"
-                    % (args.replicas, args.chain_steps),
-        "N": N_BOARD, "mcmc_type": "full_3d", "schedules": [s["type"] for s in SCHEDULES],
-        "replicas_per_schedule_per_gpu": args.replicas, "chains_total": args.replicas * len(SCHEDULES) * world,
+        "workload": wl["name"] % (args.replicas, args.chain_steps),
+        "N": wl["n"], "mcmc_type": wl["mode"], "schedules": sorted({s["type"] for s in wl["schedules"]}), "schedule_groups": ng,
+        "replicas_per_schedule_per_gpu": args.replicas, "chains_total": args.replicas * ng * world,
         "chain_steps": args.chain_steps, "history": "per-schedule sum E / sum E^2 per step (stats) + per-chain results",
-        "l2": "flushed between timed passes (256 MiB write)" if not cpu else "n/a",
         "parallelism": f"replica-sharded x{world}",
     }
+
+
+def i_alg(p):
+    """algorithmic warp-instructions per proposal of the speculative mapping at acceptance p."""
+    p = max(float(p), 1e-9)
+    return 54.0 * p / (1.0 - (1.0 - p) ** 32) + 2.0 + 70.0 * p
 
 
 # ----------------------------------------------------------------------------------------------
@@ -190,13 +219,19 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--replicas", type=int, default=REPLICAS, help="replicas per schedule per GPU")
-    ap.add_argument("--chain-steps", type=int, default=CHAIN_STEPS, help="proposals per chain per pass")
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--replicas", type=int, default=0, help="replicas per schedule per GPU (default: the workload's)")
+    ap.add_argument("--chain-steps", type=int, default=0, help="proposals per chain per pass (default: the workload's)")
     ap.add_argument("--cpu-steps", type=int, default=20000, help="proposals per chain in the CPU sample")
-    ap.add_argument("--lanes", type=int, default=0)
+    ap.add_argument("--segments", type=int, default=0,
+                    help="segments per pass whose statistics are reduced under the next segment's kernels (default: 4 when N>1, else 1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-api-e2e", action="store_true")
     args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    args.replicas = args.replicas or wl["replicas"]
+    args.chain_steps = args.chain_steps or wl["chain_steps"]
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -222,35 +257,54 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
         dist.barrier()
     import monte_carlo_collective_b200 as mcq
-    from monte_carlo_collective_b200 import schedules
 
     eng = mcq.Engine(local)
-    ns, reps, ng = args.chain_steps, args.replicas, len(SCHEDULES)
+    n, mode, scheds = wl["n"], wl["mode"], wl["schedules"]
+    ns, reps, ng = args.chain_steps, args.replicas, len(scheds)
     nc = reps * ng
     dev = torch.device(f"cuda:{local}")
+    n_seg = args.segments or (4 if world > 1 else 1)
+    bounds = [min(ns, (ns * k // n_seg) // 32 * 32) for k in range(n_seg)] + [ns]
 
     # ---- synthetic inputs ----
-    seeds_h = chain_seeds(rank, reps)
+    seeds_h = chain_seeds(args.workload, rank, reps)
     groups_h = np.repeat(np.arange(ng, dtype=np.int32), reps)
     seeds_d = torch.from_numpy(seeds_h.view(np.int64)).to(dev)
     groups_d = torch.from_numpy(groups_h).to(dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream()
     out_d = {}
+    keep = ("stat_sum_e", "stat_sum_e2", "best_energy", "final_energy", "steps_to_best", "n_accepted", "steps_done",
+            "initial_energy", "final_state", "best_state", "accept_hist", "n_near_threshold", "n_fp32_flips", "record")
 
     def device_pass():
-        r = eng.run("full_3d", N_BOARD, ns, seeds_d, schedules=SCHEDULES, groups=groups_d, history="stats",
-                    n_bins=100, device_buffers=True, lanes_per_chain=args.lanes, stream=stream.cuda_stream, out=out_d)
-        for k in ("stat_sum_e", "stat_sum_e2", "best_energy", "final_energy", "steps_to_best", "n_accepted",
-                  "steps_done", "initial_energy", "final_state", "best_state", "accept_hist"):
-            out_d[k] = getattr(r, k)
+        """One pass = n_seg segments of the schedule.  With N>1 the statistics columns of a finished segment are
+        all-reduced (NCCL, asynchronous) while the next segment's kernels run; the last segment's reduction and the
+        scalar reductions are the only communication left exposed."""
+        r, works, ms, launches, near, flips = None, [], 0.0, 0, 0, 0
+        for k in range(n_seg):
+            stop = bounds[k + 1]
+            r = eng.run(mode, n, ns, seeds_d, schedules=scheds, groups=groups_d, history="stats", n_bins=100, device_buffers=True,
+                        stream=stream.cuda_stream, out=out_d, resume=r, stop_step=stop if stop < ns else None)
+            ms += r.kernel_ms
+            launches += r.gpu_launches
+            near = near + r.n_near_threshold.sum(dtype=torch.int64)      # (per-segment counters)
+            flips = flips + r.n_fp32_flips.sum(dtype=torch.int64)
+            for name in keep:
+                out_d[name] = getattr(r, name)
+            if world > 1:
+                lo = 0 if k == 0 else bounds[k] + 1
+                for g in range(ng):
+                    works.append(dist.all_reduce(r.stat_sum_e[g, lo:stop + 1], op=dist.ReduceOp.SUM, async_op=True))
+                    works.append(dist.all_reduce(r.stat_sum_e2[g, lo:stop + 1], op=dist.ReduceOp.SUM, async_op=True))
         if world > 1:   # the only exchange of the path: final reductions over NCCL
-            dist.all_reduce(r.stat_sum_e, op=dist.ReduceOp.SUM)
-            dist.all_reduce(r.stat_sum_e2, op=dist.ReduceOp.SUM)
             gmin = r.best_energy.min().reshape(1)
-            dist.all_reduce(gmin, op=dist.ReduceOp.MIN)
+            works.append(dist.all_reduce(gmin, op=dist.ReduceOp.MIN, async_op=True))
             acc = r.n_accepted.sum(dtype=torch.int64).reshape(1)
-            dist.all_reduce(acc, op=dist.ReduceOp.SUM)
+            works.append(dist.all_reduce(acc, op=dist.ReduceOp.SUM, async_op=True))
+            for w in works:
+                w.wait()
+        r.kernel_ms, r.gpu_launches, r.band = ms, launches, torch.stack([near, flips])
         return r
 
     def sync_all():
@@ -284,30 +338,36 @@ def main():
     value = proposals_per_pass * args.steps / (total_ms * 1e-3)
     gmin = r.best_energy.min().to(torch.int64).reshape(1)
     gacc = r.n_accepted.sum(dtype=torch.int64).reshape(1)
+    local_acc = float(gacc.item())
+    band = r.band.clone()
     if world > 1:   # job-wide figures for the report line (the timed reduction is inside device_pass)
         dist.all_reduce(gmin, op=dist.ReduceOp.MIN)
         dist.all_reduce(gacc, op=dist.ReduceOp.SUM)
+        dist.all_reduce(band, op=dist.ReduceOp.SUM)
     best_min = int(gmin.item())
     acc_rate = float(gacc.item()) / (nc * ns * world)
+    # acceptance per (schedule, 1 % bin of the run) on THIS rank: the per-phase figure behind the binned roofline
+    hist = r.accept_hist.to(torch.float64).reshape(ng, reps, -1).sum(dim=1).cpu().numpy()            # [ng, 100]
+    from monte_carlo_collective_b200.engine import bin_starts
+    widths = np.diff(bin_starts(ns, 100)).astype(np.float64)
+    p_bins = hist / np.maximum(widths[None, :] * reps, 1.0)
 
     # ---- end to end through the host-buffer API ----
     e2e = None
     if not args.no_e2e:
         out_h = {}
-        h2d = seeds_h.nbytes + groups_h.nbytes + 32 * ng   # seeds, group ids, five schedule parameter records
+        h2d = seeds_h.nbytes + groups_h.nbytes + 32 * ng   # seeds, group ids, schedule parameter records
         times = []
         for it in range(min(args.warmup, 1) + args.steps):
             sync_all()
             t0 = time.perf_counter()
-            rh = eng.run("full_3d", N_BOARD, ns, seeds_h, schedules=SCHEDULES, groups=groups_h,
-                         history="stats", n_bins=100, lanes_per_chain=args.lanes, out=out_h)
+            rh = eng.run(mode, n, ns, seeds_h, schedules=scheds, groups=groups_h, history="stats", n_bins=100, out=out_h)
             sync_all()
             dt = time.perf_counter() - t0
             if it >= min(args.warmup, 1):
                 times.append(dt)
-            for k in ("stat_sum_e", "stat_sum_e2", "best_energy", "final_energy", "steps_to_best", "n_accepted",
-                      "steps_done", "initial_energy", "final_state", "best_state", "accept_hist"):
-                out_h[k] = getattr(rh, k)
+            for name in keep:
+                out_h[name] = getattr(rh, name)
         d2h = sum(out_h[k].nbytes for k in out_h)
         tmax = torch.tensor([sum(times)], dtype=torch.float64, device=dev)
         if world > 1:
@@ -316,56 +376,86 @@ def main():
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "api": "Engine.run(host NumPy buffers) -> mcq_run(MCQ_MEM_HOST)"}
 
-    # ---- roofline of the dominant kernel (spec_kernel<FULL>), DESIGN.md section 4 ----
-    # Bound: SM issue slots (4 warp-instructions / clk / SM).  Algorithmic warp-instructions per proposal of
-    # the speculative mapping: a round of 32 lanes costs 54 and retires
-    # adv(p) = (1-(1-p)^32)/p proposals at acceptance probability p; the random words of a step cost
-    # 64/32 (one Philox4x32-10 call + ring store per lane per 32 consumed steps); an accepted move costs 70.
+    # ---- the reference's own call through the drop-in API (full histories and accept bitmaps to the host) ----
+    e2e_api = None
+    if not args.no_api_e2e and world == 1 and args.workload == "c2":
+        runs, sp = reps, scheds[1]
+        best_t, n_bytes, min_best = None, 0, None
+        for _ in range(2):
+            t0 = time.perf_counter()
+            hist_rows, best_e, _times, acc_l, rej_l, _s2b = mcq.run_experiment(
+                n, ns, "random", None, runs, base_seed=BASE_SEED, schedule_params=sp, mcmc_type=mode, early_stop_patience=None)
+            dt = time.perf_counter() - t0
+            n_bytes = hist_rows[0].base.nbytes + acc_l[0]._words.base.nbytes
+            best_t = dt if best_t is None else min(best_t, dt)
+            min_best = int(min(best_e))
+            del hist_rows, acc_l, rej_l
+        e2e_api = {"value": runs * ns / best_t, "unit": "proposals/s", "seconds": best_t, "d2h_bytes": int(n_bytes),
+                   "call": f"run_experiment(N={n}, n_steps={ns}, 'random', None, n_runs={runs}, schedule_params=linear 1->3, mcmc_type='{mode}')",
+                   "returns": "uint16 history rows (views of one pinned array), bitmap-backed accepted / rejected step lists, "
+                              "best energies, steps to best -- every chain, on the host", "min_best_energy": min_best}
+
+    # ---- roofline of the dominant kernel ----
+    # Bound: SM issue slots (4 warp-instructions / clk / SM).  c2 runs fast_kernel (speculative conflict table):
+    # algorithmic warp-instructions per proposal I_alg(p) = 54/adv(p) + 2 + 70 p.  `frac`
+    # keeps round 1's definition (p = the run's overall acceptance); `frac_binned` applies the same formula per
+    # (schedule, 1 % bin of the run) with the acceptance measured there and averages over the proposals -- what the
+    # mapping algorithmically needs for THIS anneal, whose hot first phase costs several times the cold tail.
     kernel_pps = nc * ns * args.steps / (kernel_ms * 1e-3)        # this rank's kernel-only rate (CUDA events in mcq_run)
     f_mhz = clk["sm_mhz"] or 1965.0
     peak = ISSUE_PER_CLK_PER_SM * eng.sm_count * f_mhz * 1e6
-    p_acc = max(acc_rate, 1e-6)
-    p_round = 1.0 - (1.0 - p_acc) ** 32
-    i_alg = 54.0 * p_acc / p_round + 2.0 + 70.0 * p_acc
-    achieved = kernel_pps * i_alg
     peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
     hbm_peak = json.load(open(peaks_file))["hbm_gbs"] if os.path.isfile(peaks_file) else 6650.0
+    as_built = json.load(open(AS_BUILT_FILE)) if os.path.isfile(AS_BUILT_FILE) else {}
+    if args.workload == "c2":
+        ia = i_alg(acc_rate)
+        ia_binned = float(np.mean([[i_alg(p) for p in row] for row in p_bins]))
+        kernel_name = "fast_kernel<FULL=1,NR=5,LPC=32,N=12,HK=stats>"
+        formula = "54/adv(p) + 2 + 70*p, adv(p) = (1-(1-p)^32)/p, p = measured acceptance rate"
+    else:
+        ia = ia_binned = I_ALG_SURVEY[mode]
+        kernel_name = "wide_kernel (CTA per chain, line counters)" if n > 21 else "fast_kernel (board)"
+        formula = "SURVEY 8(d): 40 warp-instructions per board proposal, one warp per chain"
+    stat_bytes = 16.0 * local_acc                          # two 8-byte reductions per accepted move
     roofline = {
-        "bound": "issue", "achieved": achieved / 1e9, "peak": peak / 1e9, "unit": "Gwarp-inst/s",
-        "frac": achieved / peak, "traffic": AS_BUILT["dram_bytes_per_launch"],
-        "kernel": "spec_kernel<FULL=1,REPLAY=0,EARLY=0,NR=5,LPC=32,N=12,HIST=u16>", "i_alg_warp_inst_per_proposal": i_alg,
-        "i_alg_formula": "54/adv(p) + 2 + 70*p, adv(p) = (1-(1-p)^32)/p, p = measured acceptance rate",
+        "bound": "issue", "achieved": kernel_pps * ia / 1e9, "peak": peak / 1e9, "unit": "Gwarp-inst/s",
+        "frac": kernel_pps * ia / peak, "frac_binned": kernel_pps * ia_binned / peak,
+        "traffic": as_built.get("dram_bytes_per_launch"), "traffic_source": as_built.get("source"),
+        "kernel": kernel_name, "i_alg_warp_inst_per_proposal": ia, "i_alg_binned": ia_binned, "i_alg_formula": formula,
         "kernel_proposals_per_s": kernel_pps, "sm_clock_mhz_used": f_mhz, "sm_count": eng.sm_count,
-        "as_built": AS_BUILT,
-        "frac_under_survey_mapping": kernel_pps * I_ALG["full_3d"] / peak,
-        # shared-memory utilisation with the survey's W_alg = 3 + 1/(N-1) + 3 p wavefronts per proposal
-        "smem_util_survey": kernel_pps * (3.0 + 1.0 / 11.0 + 3.0 * p_acc) / (eng.sm_count * f_mhz * 1e6),
-        "hbm": {"algorithmic_bytes_per_proposal": 2.0, "achieved_gbs": kernel_pps * 2.0 / 1e9, "peak_gbs": hbm_peak,
+        "as_built": as_built,
+        "frac_under_survey_mapping": kernel_pps * I_ALG_SURVEY[mode] / peak,
+        "hbm": {"algorithmic_bytes_per_pass": stat_bytes,
+                "note": "statistics mode keeps no history: HBM / L2 see two 8-byte reductions per ACCEPTED move",
+                "achieved_gbs": stat_bytes * args.steps / (kernel_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
                 "peak_source": "MEASURED_PEAKS.json" if os.path.isfile(peaks_file) else "fallback"},
         "note": "frac = pps * I_alg(p) / (4 * n_SM * f_measured); as_built = ncu on the same kernel (profiles/); "
-                "frac_under_survey_mapping uses SURVEY 8(d)'s one-warp-per-chain I_alg = 48, which the speculative "
-                "conflict-table mapping is designed to beat (hence > 1)",
+                "frac_under_survey_mapping uses SURVEY 8(d)'s one-warp-per-chain estimate, which the speculative mapping is "
+                "designed to beat (hence > 1)",
     }
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = len(os.sched_getaffinity(0))
-        cpu_pps, dt, _ = cpu_pass(cores, args.cpu_steps)
+        cpu_pps, dt, _ = cpu_pass(args.workload, cores, args.cpu_steps)
         cpu_baseline = {"value": cpu_pps, "unit": "proposals/s", "cores": cores, "kind": "port",
-                        "sample": f"{cores} chains x {args.cpu_steps} proposals (schedules round-robin), N=12 full_3d, "
-                                  f"{dt:.1f} s wall, oracle/queens_numpy.py (NumPy restatement of the reference)"}
+                        "sample": f"{cores} chains x {args.cpu_steps} proposals (schedules round-robin), N={n} {mode}, {dt:.1f} s wall; {CPU_KIND_NOTE}"}
 
     if rank == 0:
         line = {
             "metric": "MCMC proposals/sec", "value": value, "unit": "proposals/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u16 conflict table / u8 counters, i32 energy, f32 accept with f64 rule inside the error band",
             "data": "synthetic", "config": workload_config(args, world),
-            "clocks": clk, "e2e": e2e, "gpu_launches": launches,
+            "l2_policy": "flushed between timed passes (256 MiB write)",
+            "clocks": clk, "e2e": e2e, "e2e_api": e2e_api, "gpu_launches": launches,
             "roofline": roofline, "cpu_baseline": cpu_baseline,
             "min_energy_reached": best_min, "acceptance_rate": acc_rate,
+            "accept_band": {"decisions_in_float64": int(band[0].item()), "float32_would_have_flipped": int(band[1].item()),
+                            "proposals": nc * ns * world},
+            "segments_per_pass": n_seg,
             "metric_full": "MCMC proposals/sec (N=12, 1/2/4/8 B200) vs host-CPU ref; min energy reached",
-            "dtype_note": "uint8 conflict table, int32 energies, float32 ex2 accept threshold on a 32-bit uniform word",
         }
         emit(line)
     if world > 1:

@@ -53,7 +53,7 @@ __device__ __forceinline__ double sched_beta64(const SchedDev &sp, int n_steps, 
 
 // float32 table of c_s = -beta_s * log2(e) for every (group, step), from the schedule parameters or from a
 // float64 table of beta (closures tabulated on the host): what the fast path of every kernel reads.
-__global__ void beta_table_kernel(const SchedDev *sched, const double *beta64, int n_groups, int n_steps, float *out) {
+static __global__ void beta_table_kernel(const SchedDev *sched, const double *beta64, int n_groups, int n_steps, float *out) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long long)n_groups * n_steps) return;
     const int g = (int)(idx / n_steps), s = (int)(idx - (long long)g * n_steps);
@@ -88,7 +88,7 @@ __device__ __forceinline__ bool metropolis_exact(const SchedDev *sched, const do
 }
 
 // the same rule as a real call: for kernels whose register budget the inlined float64 code would strain
-__device__ __noinline__ bool metropolis_exact_call(const SchedDev *sched, const double *beta64, int n_steps, int grp,
+static __device__ __noinline__ bool metropolis_exact_call(const SchedDev *sched, const double *beta64, int n_steps, int grp,
                                                    uint32_t key0, uint32_t key1, int s, int dE, uint32_t z) {
     return metropolis_exact(sched, beta64, n_steps, grp, key0, key1, s, dE, z);
 }

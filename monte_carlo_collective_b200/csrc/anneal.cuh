@@ -588,7 +588,7 @@ __global__ void __launch_bounds__(G == 1 ? 128 : 256, G == 1 ? 3 : 1) anneal_ker
 }
 
 // Builds the global-memory slabs (counters, packed state, occupancy) and the initial energies: one warp per chain.
-__global__ void __launch_bounds__(32) gslab_build_kernel(const __grid_constant__ KArgs a) {
+static __global__ void __launch_bounds__(32) gslab_build_kernel(const __grid_constant__ KArgs a) {
     const int chain = a.chain_begin + blockIdx.x;
     if (chain >= a.n_chains) return;
     const int e = build_chain<32>(a, a.gslab + (size_t)chain * a.lay.stride, a.state + (size_t)chain * a.state_bytes, true, threadIdx.x);

@@ -18,12 +18,13 @@
 
 #include "../../include/mcq.h"
 #include "anneal.cuh"
-#include "wide.cuh"
+#include "geometry.cuh"
+#include "launch.h"
 
 namespace mcq {
 
 static thread_local std::string g_err;
-static int g_smem_optin = 227 * 1024;   // sharedMemPerBlockOptin of the device (set by mcq_create)
+int g_smem_optin = 227 * 1024;   // sharedMemPerBlockOptin of the device (set by mcq_create)
 
 static int fail(int code, const std::string &msg) {
     g_err = msg;
@@ -356,125 +357,6 @@ struct mcq_ctx {
 };
 
 namespace mcq {
-
-template <int G, bool FULL, bool REPLAY>
-static cudaError_t launch_one(const KArgs &a, int grid, int block, size_t smem, cudaStream_t s) {
-    auto k = anneal_kernel<G, FULL, REPLAY>;
-    // always the device maximum: the attribute is per function and per device, so concurrent host threads
-    // (one engine each) must not race different values into it
-    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin);
-    if (e != cudaSuccess) return e;
-    k<<<grid, block, smem, s>>>(a);
-    return cudaGetLastError();
-}
-
-template <int G>
-static cudaError_t launch_g(const KArgs &a, bool replay, int grid, int block, size_t smem, cudaStream_t s) {
-    if (a.full) return replay ? launch_one<G, true, true>(a, grid, block, smem, s) : launch_one<G, true, false>(a, grid, block, smem, s);
-    return replay ? launch_one<G, false, true>(a, grid, block, smem, s) : launch_one<G, false, false>(a, grid, block, smem, s);
-}
-
-template <bool FULL, bool REPLAY, bool EARLY, int NR, int LPC, int CN = 0, int HK = -1>
-static cudaError_t launch_spec_one(const KArgs &a, int grid, int block, size_t smem, cudaStream_t s) {
-    auto k = spec_kernel<FULL, REPLAY, EARLY, NR, LPC, CN, HK>;
-    // always the device maximum: the attribute is per function and per device, so concurrent host threads
-    // (one engine each) must not race different values into it
-    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin);
-    if (e != cudaSuccess) return e;
-    k<<<grid, block, smem, s>>>(a);
-    return cudaGetLastError();
-}
-
-// the board sizes the reference's experiments use are compiled in altogether (N, Q = N^2 and the slab geometry
-// become immediates: ~25 fewer instructions per round); other sizes take the geometry from the arguments
-template <bool FULL, int CN>
-static cudaError_t launch_spec_cn(const KArgs &a, int grid, int block, size_t smem, cudaStream_t s) {
-    constexpr int NR = spec_layout(FULL, CN, CN * CN).rounds;
-    // ... and the per-step output with it: nothing, the statistics in difference form, or a uint16 history
-    // (callers check fixed_n_serves() first: other combinations run the kernels that take the geometry at run time)
-    if (a.hist_kind == MCQ_HIST_U16) return launch_spec_one<FULL, false, false, NR, 32, CN, 1>(a, grid, block, smem, s);
-    if (a.dsum_e) return launch_spec_one<FULL, false, false, NR, 32, CN, 3>(a, grid, block, smem, s);   // (row offsets are 32-bit there)
-    return launch_spec_one<FULL, false, false, NR, 32, CN, 0>(a, grid, block, smem, s);
-}
-static inline bool fixed_n_serves(const KArgs &a) {
-    if (a.dsum_e && !a.stat_rows32) return false;
-    return a.hist_kind == MCQ_HIST_NONE || (a.hist_kind == MCQ_HIST_U16 && !a.dsum_e);
-}
-
-// production kernels have the neighbour-row length compiled in; replay / early-stop ones take it at run time
-template <bool FULL, int LPC>
-static cudaError_t launch_spec_nr(const KArgs &a, int grid, int block, size_t smem, cudaStream_t s) {
-    if (LPC == 32 && a.Q == a.N * a.N && fixed_n_serves(a) && !getenv("MCQ_NO_FIXED_N")) {
-        switch (a.N) {
-            case 8: return launch_spec_cn<FULL, 8>(a, grid, block, smem, s);
-            case 9: return launch_spec_cn<FULL, 9>(a, grid, block, smem, s);
-            case 10: return launch_spec_cn<FULL, 10>(a, grid, block, smem, s);
-            case 11: return launch_spec_cn<FULL, 11>(a, grid, block, smem, s);
-            case 12: return launch_spec_cn<FULL, 12>(a, grid, block, smem, s);
-            case 13: return launch_spec_cn<FULL, 13>(a, grid, block, smem, s);
-            case 14: return launch_spec_cn<FULL, 14>(a, grid, block, smem, s);
-            case 15: return launch_spec_cn<FULL, 15>(a, grid, block, smem, s);
-            case 16: return launch_spec_cn<FULL, 16>(a, grid, block, smem, s);
-            case 20: if (!FULL) return launch_spec_cn<false, 20>(a, grid, block, smem, s); break;
-            default: break;
-        }
-    }
-    switch (a.sl.rounds) {
-        case 1: return launch_spec_one<FULL, false, false, 1, LPC>(a, grid, block, smem, s);
-        case 2: return launch_spec_one<FULL, false, false, 2, LPC>(a, grid, block, smem, s);
-        case 3: return launch_spec_one<FULL, false, false, 3, LPC>(a, grid, block, smem, s);
-        case 4: return launch_spec_one<FULL, false, false, 4, LPC>(a, grid, block, smem, s);
-        case 5: return launch_spec_one<FULL, false, false, 5, LPC>(a, grid, block, smem, s);
-        case 6: return launch_spec_one<FULL, false, false, 6, LPC>(a, grid, block, smem, s);
-        case 7: return launch_spec_one<FULL, false, false, 7, LPC>(a, grid, block, smem, s);
-        default: return launch_spec_one<FULL, false, false, 8, LPC>(a, grid, block, smem, s);
-    }
-}
-
-template <int LPC>
-static cudaError_t launch_spec_lpc(const KArgs &a, bool replay, int grid, int block, size_t smem, cudaStream_t s) {
-    if (a.full) return replay ? launch_spec_one<true, true, false, 0, LPC>(a, grid, block, smem, s) : launch_spec_nr<true, LPC>(a, grid, block, smem, s);
-    if (a.patience >= 0) return replay ? launch_spec_one<false, true, true, 0, LPC>(a, grid, block, smem, s) : launch_spec_one<false, false, true, 0, LPC>(a, grid, block, smem, s);
-    return replay ? launch_spec_one<false, true, false, 0, LPC>(a, grid, block, smem, s) : launch_spec_nr<false, LPC>(a, grid, block, smem, s);
-}
-
-template <bool FULL, bool EARLY, int NT>
-static cudaError_t launch_wide_one(const KArgs &a, int grid, size_t smem, cudaStream_t s) {
-    auto k = wide_kernel<FULL, EARLY, NT>;
-    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin);
-    if (e != cudaSuccess) return e;
-    k<<<grid, NT, smem, s>>>(a);
-    return cudaGetLastError();
-}
-
-template <int NT>
-static cudaError_t launch_wide_nt(const KArgs &a, int grid, size_t smem, cudaStream_t s) {
-    if (a.full) return launch_wide_one<true, false, NT>(a, grid, smem, s);
-    return a.patience >= 0 ? launch_wide_one<false, true, NT>(a, grid, smem, s) : launch_wide_one<false, false, NT>(a, grid, smem, s);
-}
-
-static cudaError_t launch_wide(int threads, const KArgs &a, int grid, size_t smem, cudaStream_t s) {
-    switch (threads) {
-        case 32: return launch_wide_nt<32>(a, grid, smem, s);
-        case 64: return launch_wide_nt<64>(a, grid, smem, s);
-        case 128: return launch_wide_nt<128>(a, grid, smem, s);
-        default: return launch_wide_nt<256>(a, grid, smem, s);
-    }
-}
-
-static cudaError_t launch_spec(int lpc, const KArgs &a, bool replay, int grid, int block, size_t smem, cudaStream_t s) {
-    return lpc == 16 ? launch_spec_lpc<16>(a, replay, grid, block, smem, s) : launch_spec_lpc<32>(a, replay, grid, block, smem, s);
-}
-
-static cudaError_t launch_anneal(int G, const KArgs &a, bool replay, int grid, int block, size_t smem, cudaStream_t s) {
-    switch (G) {
-        case 1: return launch_g<1>(a, replay, grid, block, smem, s);
-        case 4: return launch_g<4>(a, replay, grid, block, smem, s);
-        case 8: return launch_g<8>(a, replay, grid, block, smem, s);
-        case 16: return launch_g<16>(a, replay, grid, block, smem, s);
-        default: return launch_g<32>(a, replay, grid, block, smem, s);
-    }
-}
 
 static int check_problem(int mode, int n, int q) {
     if (mode != MCQ_MODE_BOARD && mode != MCQ_MODE_FULL3D) return fail(MCQ_EINVAL, "mode must be MCQ_MODE_BOARD or MCQ_MODE_FULL3D");
@@ -846,15 +728,26 @@ int mcq_run(mcq_ctx *ctx, const mcq_run_params *p) {
         // Lane groups of 16 or 32 per chain.  Registers (64/thread) allow 32 warps per SM; shared memory may allow
         // fewer.  All CTAs of a launch take the same time, so a launch costs ceil(waves) full waves: pick the
         // (group width, resident CTAs per SM) pair with the best modelled rate x wave efficiency.
-        if (wpc > 4) return fail(MCQ_EINVAL, "the conflict-table kernel runs at most 4 warps per CTA");
-        const int w = wpc ? wpc : 4;
+        // (fast_serves needs the launch arguments; the geometry decisions below only need to know which kernel it will be)
+        KArgs probe;
+        memset(&probe, 0, sizeof probe);
+        probe.full = full; probe.N = p->n; probe.Q = p->q; probe.patience = (!full && p->early_stop_patience >= 0) ? p->early_stop_patience : -1;
+        probe.hist_kind = want_hist ? p->hist_dtype : MCQ_HIST_NONE;
+        probe.dsum_e = want_stats ? reinterpret_cast<unsigned long long *>(1) : nullptr;
+        probe.stat_rows32 = (long long)p->n_groups * ((long long)ns + 1) < (1LL << 31);
+        const int lpc_req = (p->algo == MCQ_ALGO_TABLE && p->lanes_per_chain == 16) ? 16 : 32;
+        const bool fast = fast_serves(lpc_req, probe, replay);
+        const int w_max = fast && lpc_req == 32 ? MCQ_FAST_WARPS : 4, w_def = w_max;
+        const int minb = lpc_req != 32 ? 5 : fast ? MCQ_FAST_MINB : MCQ_SPEC_MINB;
+        if (wpc > w_max) return fail(MCQ_EINVAL, "the conflict-table kernel does not run that many warps per CTA");
+        const int w = wpc ? wpc : w_def;
         const int sms = ctx->prop.multiProcessorCount;
         auto cta_smem = [&](int lpc) { return (size_t)sl.cta_bytes + (size_t)w * (32 / lpc) * sl.stride; };
         auto max_ctas = [&](int lpc) {   // residency limit: registers, warps, shared memory
             const size_t need = cta_smem(lpc);
             if (need > smem_block) return 0;
             // registers: the kernel is compiled for MCQ_SPEC_MINB CTAs of 4 warps per SM
-            return (int)std::min<size_t>((size_t)((lpc == 32 ? MCQ_SPEC_MINB : 5) * 4 / w), smem_sm / (round_up((int)need, 1024) + 1024));
+            return (int)std::min<size_t>((size_t)(minb * w_max / w), smem_sm / (round_up((int)need, 1024) + 1024));
         };
         // relative throughput of one SM vs resident warps (measured, N=12 full_3d, single full wave)
         auto rate = [&](int lpc, int warps) {
@@ -964,7 +857,9 @@ int mcq_run(mcq_ctx *ctx, const mcq_run_params *p) {
             a.beta64 = static_cast<double *>(d);
         }
         const long long cells = (long long)p->n_groups * ns;
-        if (ctx->buf[B_BETA].ensure((size_t)cells * 4)) return fail(MCQ_ENOMEM, "device allocation failed (schedule table)");
+        // (padded: the lanes of a round that reach past the end of a launch read, and discard, up to 32 entries more)
+        if (ctx->buf[B_BETA].ensure((size_t)(cells + BETA_PAD) * 4)) return fail(MCQ_ENOMEM, "device allocation failed (schedule table)");
+        CUDA_TRY(cudaMemsetAsync(static_cast<float *>(ctx->buf[B_BETA].p) + cells, 0, BETA_PAD * 4, s));
         beta_table_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, s>>>(a.sched, a.beta64, p->n_groups, ns, static_cast<float *>(ctx->buf[B_BETA].p));
         CUDA_TRY(cudaGetLastError());
         ++launches;
@@ -1014,8 +909,7 @@ int mcq_run(mcq_ctx *ctx, const mcq_run_params *p) {
         CUDA_TRY(cudaMemsetAsync(a.gslab + (size_t)nc * lay.stride, 0, lay.stride, s));
         a.chain_begin = 0;
         a.t_begin = t_start;
-        gslab_build_kernel<<<nc, 32, 0, s>>>(a);
-        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(launch_gslab_build(a, nc, s));
         ++launches;
     }
 
@@ -1159,7 +1053,8 @@ int mcq_run(mcq_ctx *ctx, const mcq_run_params *p) {
             if (hi <= lo) continue;
             cudaStream_t sb = sub_stream[b];
             a.chain_begin = lo; a.n_chains = hi;
-            CUDA_TRY(use_spec ? launch_spec(spec_lpc, a, replay, cta_hi - cta_lo, block, smem, sb)
+            CUDA_TRY(use_spec ? (fast_serves(spec_lpc, a, replay) ? launch_fast(spec_lpc, a, cta_hi - cta_lo, block, smem, sb)
+                                                                  : launch_spec(spec_lpc, a, replay, cta_hi - cta_lo, block, smem, sb))
                      : use_wide ? launch_wide(wide_threads, a, cta_hi - cta_lo, smem, sb)
                                 : launch_anneal(G, a, replay, cta_hi - cta_lo, block, smem, sb));
             ++launches;

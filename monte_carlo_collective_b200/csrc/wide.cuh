@@ -23,14 +23,13 @@
 // Random stream, proposal rule and Metropolis test are those of anneal_kernel, bit for bit: the same seeds give
 // the same trajectory on either kernel (tests/test_gpu_production.py).
 #pragma once
+#include "launch.h"
 #include "spec.cuh"
 
 namespace mcq {
 
-constexpr int WIDE_THREADS = 256;             // widest CTA (one per SM on the largest boards); 128 and 64 where more CTAs fit
-// (the ring of random words keeps 2 * blockDim steps)
-constexpr int WIDE_JCAP = 62;                 // journal of state elements changed since the last best-state snapshot
-constexpr int WIDE_XCH_BYTES = 384;           // exchange words (3 per warp), journal count, journal, published moves (3 words per warp)
+// WIDE_THREADS, WIDE_JCAP, WIDE_XCH_BYTES: launch.h (the host sizes shared memory with them);
+// the ring of random words keeps 2 * blockDim steps
 
 template <bool FULL, bool EARLY, int NT>
 __global__ void __launch_bounds__(NT, 1) wide_kernel(const __grid_constant__ KArgs a) {

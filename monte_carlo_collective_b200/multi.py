@@ -143,7 +143,8 @@ class DevicePool:
             if hi <= lo:
                 return None
             out = {k: whole[k][lo:hi] for k in per_chain}
-            return self.engine(self.devices[d]).run(
+            # (slot d: a device listed twice gets two engines -- an engine serves one thread at a time)
+            return self.engine(self.devices[d], slot=d).run(
                 mcmc_type, n, ns, seeds[lo:hi], betas, groups=None if groups is None else groups[lo:hi],
                 init_states=None if init_states is None else init_states[lo:hi], out=out, **common)
 
