@@ -61,7 +61,7 @@ extern "C" {
 
 /* delta-E data structure / kernel */
 #define MCQ_ALGO_AUTO 0   /* conflict table up to N = 18 (full_3d) / 21 (board), else one CTA per chain on line counters;
-                             replays and short runs of very many large-board chains use LINES / GMEM */
+                             replays of large boards use LINES / GMEM */
 #define MCQ_ALGO_LINES 1  /* per-line occupancy counters, `lanes_per_chain` lanes per chain (anneal.cuh) */
 #define MCQ_ALGO_TABLE 2  /* per-cell conflict table, one warp per chain, speculative rounds (spec.cuh) */
 #define MCQ_ALGO_GMEM 3   /* line counters in global memory, one thread per chain: boards too large for shared memory */

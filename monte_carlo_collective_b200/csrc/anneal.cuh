@@ -25,6 +25,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 #include "accept.cuh"
 #include "philox.cuh"
 
@@ -75,7 +77,8 @@ struct KArgs {
     int patience;         // < 0: none
     Layout lay;
     SLayout sl;
-    int4 coef[NFAM];      // idx = x*i + y*j + z*k + w  (w includes the family base)
+    int4 coef[NFAM];      // idx = x*i + y*j + z*k + w  (w includes the family base) ...
+    int4 csel[NFAM];      // ... + (x*i + y*j + w < 0 ? z : 0): the fold of the space-diagonal families (all zero for the others)
     // per-chain inputs
     const unsigned long long *seeds;
     const int *group;     // may be null
@@ -120,8 +123,25 @@ struct KArgs {
     const uint32_t *geo;   // conflict-table kernel, full_3d: shared-line bits then wide ids (sl.cta_bytes)
 };
 
-__device__ __forceinline__ int line_index(const int4 c, int i, int j, int k) {
-    return c.x * i + c.y * j + c.z * k + c.w;
+// Counter index of the attack line of family (c, s) through cell (i, j, k).  Axis and planar-diagonal families are
+// affine in (i, j, k).  A space-diagonal family is a hexagon of 3N^2-3N+1 lines inside the (2N-1)^2 square of
+// (a, b) = (i -+ j, i -+ k) pairs; rows a and a - N of the hexagon together are 3N-2 long, so it folds into N rows of
+// 3N-2 with idx = a(3N-3) + b + (N-1) + (a < 0 ? 3N^2-N-1 : 0): affine plus one select on the sign of a
+// (make_coefs, mcq_api.cu).  That is 25 % fewer counter bytes than the square (N = 64: 105.6 KB instead of 121.5 KB
+// per chain -- two chains per SM instead of one).
+__device__ __forceinline__ int line_index(const int4 c, const int4 s, int i, int j, int k) {
+    return c.x * i + c.y * j + c.z * k + c.w + ((s.x * i + s.y * j + s.w) < 0 ? s.z : 0);
+}
+// family known at compile time: only the four space-diagonal families (9..12) carry the select
+template <int F>
+__device__ __forceinline__ int line_index_f(const KArgs &a, int i, int j, int k) {
+    const int4 c = a.coef[F];
+    int idx = c.x * i + c.y * j + c.z * k + c.w;
+    if constexpr (F >= 9) {
+        const int4 s = a.csel[F];
+        idx += (s.x * i + s.y * j + s.w) < 0 ? s.z : 0;
+    }
+    return idx;
 }
 
 // statistics in difference form (see KArgs::dsum_e): one lane per chain calls this when the chain's energy
@@ -184,7 +204,7 @@ __device__ int build_chain(const KArgs &a, unsigned char *S, const uint8_t *ext,
                 st[qi] = (unsigned char)k;
             }
             for (int f = a.full ? 0 : 1; f < NFAM; ++f) {
-                const int idx = line_index(a.coef[f], i, j, k);
+                const int idx = line_index(a.coef[f], a.csel[f], i, j, k);
                 atomicAdd(&W[idx >> 2], 1u << ((idx & 3) * 8));
             }
         }
@@ -206,14 +226,18 @@ __device__ int build_chain(const KArgs &a, unsigned char *S, const uint8_t *ext,
 template <int G>
 struct LaneLines {
     static constexpr int R = (NFAM + G - 1) / G;
-    int4 c[R];
+    int4 c[R], s[R];
+    const KArgs *ka;   // G == 1: a thread evaluates every family, straight from the kernel arguments (no register copies)
     __device__ __forceinline__ void init(const KArgs &a, int g) {
+        ka = &a;
+        if constexpr (G == 1) return;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const int f = g + r * G;
             const bool ok = f < NFAM && (a.full || f != 0);
             // an unused slot maps old and new cell to the same counter: contributes 0, never updated
             c[r] = ok ? a.coef[f] : make_int4(0, 0, 0, 0);
+            s[r] = ok ? a.csel[f] : make_int4(0, 0, 0, 0);
         }
     }
 };
@@ -227,10 +251,25 @@ struct LineEval {
     __device__ __forceinline__ int eval(const LaneLines<G> &L, const uint8_t *cnt, int i0, int j0, int k0, int i1,
                                         int j1, int k1) {
         int d = 0;
+        if constexpr (G == 1) {
+            // families are compile-time here: board mode maps family 0 (the (i,j) column) to one counter for both cells
+            const KArgs &a = *L.ka;
+            auto both = [&](auto fc) {
+                constexpr int f = decltype(fc)::value;
+                if (f == 0 && !a.full) { io[f] = 0; in[f] = 0; }
+                else { io[f] = line_index_f<f>(a, i0, j0, k0); in[f] = line_index_f<f>(a, i1, j1, k1); }
+            };
+            both(std::integral_constant<int, 0>{}); both(std::integral_constant<int, 1>{}); both(std::integral_constant<int, 2>{});
+            both(std::integral_constant<int, 3>{}); both(std::integral_constant<int, 4>{}); both(std::integral_constant<int, 5>{});
+            both(std::integral_constant<int, 6>{}); both(std::integral_constant<int, 7>{}); both(std::integral_constant<int, 8>{});
+            both(std::integral_constant<int, 9>{}); both(std::integral_constant<int, 10>{}); both(std::integral_constant<int, 11>{});
+            both(std::integral_constant<int, 12>{});
+        } else {
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-            io[r] = line_index(L.c[r], i0, j0, k0);
-            in[r] = line_index(L.c[r], i1, j1, k1);
+            for (int r = 0; r < R; ++r) {
+                io[r] = line_index(L.c[r], L.s[r], i0, j0, k0);
+                in[r] = line_index(L.c[r], L.s[r], i1, j1, k1);
+            }
         }
 #pragma unroll
         for (int r = 0; r < R; ++r) {

@@ -198,7 +198,11 @@ __global__ void __launch_bounds__(LPC == 32 ? 32 * MCQ_FAST_WARPS : 128, LPC == 
             const uint32_t w1 = SM16(sW + 2 * c1);
             c0 = p0 & 0xffffu;
             const uint32_t e = w1 - (p0 >> 16) + wide_bias;
+#ifdef MCQ_DBG_NOLUT    // sensitivity probe only: no shared-line correction (wrong delta-E on ~17 % of the proposals)
+            dE = (v1 & CNT) - ((int)(TE)TBL(sT, c0) & CNT) + 1 - (int)(e & 1u);
+#else
             dE = (v1 & CNT) - ((int)(TE)TBL(sT, c0) & CNT) + 1 - (int)((SM32(4 * (e >> 5)) >> (e & 31)) & 1u);
+#endif
             aux = q | (w1 << 16);
         } else {
             const uint32_t ij = __umulhi(r.x, (uint32_t)(N * N));
@@ -211,6 +215,9 @@ __global__ void __launch_bounds__(LPC == 32 ? 32 * MCQ_FAST_WARPS : 128, LPC == 
         }
         bool accept, near_band;
         metropolis_fast(dE, cb, r.z, a.band_abs, accept, near_band);
+#ifdef MCQ_DBG_NONEAR   // sensitivity probe only (not a product configuration): float32 decisions, no band
+        near_band = false;
+#endif
 
         // ---------------- the vote: most rounds of a cold chain end here ----------------
         unsigned acc_all = __ballot_sync(FULLMASK, accept && valid);

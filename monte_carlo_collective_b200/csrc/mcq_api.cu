@@ -48,12 +48,15 @@ static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
 // idx = x*i + y*j + z*k + w for the 13 line families (oracle/queens_numpy.py: line_ids).
 // Board mode has no (i,j) family; its counters start at family 1.
-static int make_coefs(int full, int N, int4 coef[NFAM]) {
+static int make_coefs(int full, int N, int4 coef[NFAM], int4 csel[NFAM]) {
     const int W = 2 * N - 1, o = N - 1;
-    const int sz_axis = N * N, sz_plane = N * W, sz_space = W * W;
+    // space-diagonal families: the hexagon of valid (a, b) pairs folded into N rows of 3N-2 (anneal.cuh: line_index)
+    const int R = 3 * N - 3, fold = 3 * N * N - N - 1;
+    const int sz_axis = N * N, sz_plane = N * W, sz_space = N * (3 * N - 2);
     int base[NFAM];
     int b = 0;
     for (int f = 0; f < NFAM; ++f) {
+        csel[f] = make_int4(0, 0, 0, 0);
         if (f == 0 && !full) { base[f] = 0; continue; }
         base[f] = b;
         b += f < 3 ? sz_axis : f < 9 ? sz_plane : sz_space;
@@ -69,17 +72,20 @@ static int make_coefs(int full, int N, int4 coef[NFAM]) {
     coef[6] = make_int4(1, W, 1, base[6]);
     coef[7] = make_int4(W, 1, -1, base[7] + o);
     coef[8] = make_int4(W, 1, 1, base[8]);
-    coef[9] = make_int4(W + 1, -W, -1, base[9] + o * W + o);
-    coef[10] = make_int4(W + 1, -W, 1, base[10] + o * W);
-    coef[11] = make_int4(W + 1, W, -1, base[11] + o);
-    coef[12] = make_int4(W + 1, W, 1, base[12]);
+    // idx = a R + b + o (+ fold when a < 0) with (a, b) = (i-j, i-k), (i-j, i+k-o), (i+j-o, i-k), (i+j-o, i+k-o)
+    coef[9] = make_int4(R + 1, -R, -1, base[9] + o);
+    coef[10] = make_int4(R + 1, -R, 1, base[10]);
+    coef[11] = make_int4(R + 1, R, -1, base[11] + o - R * o);
+    coef[12] = make_int4(R + 1, R, 1, base[12] - R * o);
+    csel[9] = csel[10] = make_int4(1, -1, fold, 0);
+    csel[11] = csel[12] = make_int4(1, 1, fold, -o);
     return b;  // total counter bytes
 }
 
 static Layout make_layout(int full, int N, int Q, int G) {
     Layout L;
-    int4 tmp[NFAM];
-    L.n_cnt = round_up(make_coefs(full, N, tmp), 4);
+    int4 tmp[NFAM], tmp2[NFAM];
+    L.n_cnt = round_up(make_coefs(full, N, tmp, tmp2), 4);
     L.pos32 = (full && N > 32) ? 1 : 0;
     L.off_state = L.n_cnt;
     int state_b = full ? Q * (L.pos32 ? 4 : 2) : N * N;
@@ -547,7 +553,7 @@ static int probe_common(mcq_ctx *ctx, int mode, int n, int q, int n_states, cons
     a.full = mode == MCQ_MODE_FULL3D;
     a.N = n; a.Q = q; a.n_chains = n_states;
     a.lay = make_layout(a.full, n, q, 32);
-    make_coefs(a.full, n, a.coef);
+    make_coefs(a.full, n, a.coef, a.csel);
     a.state_bytes = state_bytes_of(mode, n, q);
     if ((size_t)a.lay.stride > ctx->prop.sharedMemPerBlockOptin) return fail(MCQ_ENOMEM, "one chain does not fit in shared memory");
     void *d = nullptr;
@@ -662,18 +668,16 @@ int mcq_run(mcq_ctx *ctx, const mcq_run_params *p) {
     bool use_gmem = !use_spec && (p->algo == MCQ_ALGO_GMEM ||
         (p->algo == MCQ_ALGO_AUTO && G == 0 && (size_t)make_layout(full, p->n, p->q, 32).stride * MCQ_GMEM_MIN_CHAINS_PER_SM > smem_sm));
     // One CTA per chain on shared-memory line counters (wide.cuh); production runs only.  It is the default beyond
-    // the conflict table's reach: 3-20x faster than a warp or a thread per chain when the chains are few, and
-    // ahead on long anneals at any count (a cold chain retires ~60 proposals per round).  Only short, hot runs
-    // of very many chains are left to the global-memory kernel (measured crossover at N = 64: 32 chains per SM
-    // below 1e6 steps).
+    // the conflict table's reach: 3-20x faster than a warp or a thread per chain when the chains are few, ahead on
+    // long anneals at any count (a cold chain retires ~60 proposals per round), and -- since the folded
+    // space-diagonal counters let an SM hold two N = 64 chains -- level with the global-memory kernel even on
+    // short hot runs of very many chains (65536 chains x 1e5 steps at N = 64: 2.5e9 proposals/s either way).
     bool use_wide = !use_spec && p->algo == MCQ_ALGO_WIDE;
     if (use_wide && replay) return fail(MCQ_EINVAL, "MCQ_ALGO_WIDE does not replay recorded streams");
     {
         const Layout l1 = make_layout(full, p->n, p->q, 1);
-        const size_t need = (size_t)l1.off_pkt + round_up(l1.off_occ - l1.off_state, 16) + 2 * 32 * 16 + WIDE_XCH_BYTES;   // narrowest CTA
-        if (p->algo == MCQ_ALGO_AUTO && !use_spec && !replay && G == 0 && need <= smem_block &&
-            !(use_gmem && nc >= 32 * ctx->prop.multiProcessorCount && ns < 1000000))
-            use_wide = true;
+        const size_t need = (size_t)l1.off_pkt + 2 * 32 * 16 + WIDE_XCH_BYTES;   // narrowest CTA
+        if (p->algo == MCQ_ALGO_AUTO && !use_spec && !replay && G == 0 && need <= smem_block) use_wide = true;
     }
     if (use_wide) use_gmem = false;
     if (use_gmem || use_wide) G = 1;
@@ -685,7 +689,7 @@ int mcq_run(mcq_ctx *ctx, const mcq_run_params *p) {
     // CTA-per-chain kernel: 8, 4, 2 or 1 warps per chain.  A round is bound by its dependent instruction chain, so what
     // counts is how many chains an SM holds (shared memory: counters + state + a ring of 2 * threads steps;
     // registers: 128 per thread); among equals the widest CTA speculates furthest.  warps_per_cta = 1, 2, 4, 8 overrides.
-    const int w_best = lay.off_pkt, w_ring = w_best + round_up(lay.off_occ - lay.off_state, 16);
+    const int w_best = lay.off_pkt, w_ring = lay.off_pkt;   // (the best state is kept in global memory: no shared copy)
     int wide_threads = WIDE_THREADS;
     auto wide_bytes = [&](int nt) { return (size_t)w_ring + 2 * (size_t)nt * 16 + WIDE_XCH_BYTES; };
     if (use_wide) {
@@ -834,7 +838,7 @@ int mcq_run(mcq_ctx *ctx, const mcq_run_params *p) {
             a.geo = static_cast<const uint32_t *>(gb.p);
         }
     }
-    make_coefs(full, p->n, a.coef);
+    make_coefs(full, p->n, a.coef, a.csel);
     a.state_bytes = sbytes;
     void *d = nullptr;
     if (p->chain_seeds) { if (int rc = stage_in(ctx, B_SEEDS, p->chain_seeds, (size_t)nc * 8, mem, s, &d)) return rc; a.seeds = static_cast<unsigned long long *>(d); }

@@ -29,7 +29,11 @@ struct Philox4 {
 MCQ_HD Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
     const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
 #pragma unroll
+#ifdef MCQ_DBG_PHILOX7   // sensitivity probe only (not a product configuration)
+    for (int r = 0; r < 7; ++r) {
+#else
     for (int r = 0; r < 10; ++r) {
+#endif
         const uint32_t hi0 = mulhi32(M0, c0), lo0 = M0 * c0;
         const uint32_t hi1 = mulhi32(M1, c2), lo1 = M1 * c2;
         c0 = hi1 ^ c1 ^ k0;

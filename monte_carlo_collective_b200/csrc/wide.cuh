@@ -48,10 +48,9 @@ __global__ void __launch_bounds__(NT, 1) wide_kernel(const __grid_constant__ KAr
     uint8_t *cnt = smem;
     unsigned char *st = smem + a.lay.off_state;
     uint32_t *occ = reinterpret_cast<uint32_t *>(smem + a.lay.off_occ);
-    unsigned char *bst = smem + a.w_best;                             // state at the best energy (internal format)
+    uint8_t *best_out = a.best_state + (size_t)chain * a.state_bytes;   // state at the best energy: kept in global memory, external format
     uint4 *ring = reinterpret_cast<uint4 *>(smem + a.w_ring);
     int *xch = reinterpret_cast<int *>(smem + a.w_xch);               // [NW] first accepting thread per warp, [NW] its delta-E, scratch
-    const int st_bytes = a.lay.off_occ - a.lay.off_state;             // internal state bytes, rounded up to 4
     int *jcount = xch + 3 * NW;                                       // entries in the journal; > WIDE_JCAP: overflowed
     uint16_t *jrn = reinterpret_cast<uint16_t *>(xch + 3 * NW + 1);
     uint32_t *xmv = reinterpret_cast<uint32_t *>(xch) + 64;           // [NW][3]: old cell, new cell, queen of each warp's first acceptance
@@ -75,7 +74,7 @@ __global__ void __launch_bounds__(NT, 1) wide_kernel(const __grid_constant__ KAr
             }
 #pragma unroll
             for (int f = F0; f < NFAM; ++f) {
-                const int idx = line_index(a.coef[f], i, j, k);
+                const int idx = line_index(a.coef[f], a.csel[f], i, j, k);
                 atomicAdd(&W[idx >> 2], 1u << ((idx & 3) * 8));
             }
         }
@@ -107,7 +106,6 @@ __global__ void __launch_bounds__(NT, 1) wide_kernel(const __grid_constant__ KAr
     int best = E, stale = 0, n_acc = 0, best_step = 0, bin_mark = 0;
     int done = a.t_end;
     int t = a.t_begin;
-    bool snap = false;   // a new best was reached in this launch: bst holds its state
     // A new best copies only the state elements moved since the previous snapshot (hot chains set a new best
     // at almost every acceptance).  jfresh: the journal restarts at the next commit; the first snapshot of a
     // launch copies everything.
@@ -192,11 +190,18 @@ __global__ void __launch_bounds__(NT, 1) wide_kernel(const __grid_constant__ KAr
         // delta-E from the line counters: old_conf = sum(co - 1), new_conf = sum(cn) - [shared line]
         {
             int io[NFAM], in[NFAM];
-#pragma unroll
-            for (int f = F0; f < NFAM; ++f) {
-                io[f] = line_index(a.coef[f], i0, j0, k0c);
-                in[f] = line_index(a.coef[f], i1, j1, k1c);
-            }
+            auto both = [&](auto fc) {
+                constexpr int f = decltype(fc)::value;
+                if constexpr (f >= F0) {
+                    io[f] = line_index_f<f>(a, i0, j0, k0c);
+                    in[f] = line_index_f<f>(a, i1, j1, k1c);
+                }
+            };
+            both(std::integral_constant<int, 0>{}); both(std::integral_constant<int, 1>{}); both(std::integral_constant<int, 2>{});
+            both(std::integral_constant<int, 3>{}); both(std::integral_constant<int, 4>{}); both(std::integral_constant<int, 5>{});
+            both(std::integral_constant<int, 6>{}); both(std::integral_constant<int, 7>{}); both(std::integral_constant<int, 8>{});
+            both(std::integral_constant<int, 9>{}); both(std::integral_constant<int, 10>{}); both(std::integral_constant<int, 11>{});
+            both(std::integral_constant<int, 12>{});
 #pragma unroll
             for (int f = F0; f < NFAM; ++f) {
                 const int co = cnt[io[f]], cn = cnt[in[f]];
@@ -278,8 +283,8 @@ __global__ void __launch_bounds__(NT, 1) wide_kernel(const __grid_constant__ KAr
             }
             const int a0 = po & 255, b0 = (po >> 8) & 255, c0 = po >> 16, a1 = pn & 255, b1 = (pn >> 8) & 255, c1 = pn >> 16;
             if (warp == wf && lane >= F0 && lane < NFAM) {
-                const int4 cf = a.coef[lane];
-                const int o = line_index(cf, a0, b0, c0), n = line_index(cf, a1, b1, c1);
+                const int4 cf = a.coef[lane], cs = a.csel[lane];
+                const int o = line_index(cf, cs, a0, b0, c0), n = line_index(cf, cs, a1, b1, c1);
                 if (o != n) {
                     const int vo = cnt[o], vn = cnt[n];
                     cnt[o] = (uint8_t)(vo - 1); cnt[n] = (uint8_t)(vn + 1);
@@ -320,21 +325,25 @@ __global__ void __launch_bounds__(NT, 1) wide_kernel(const __grid_constant__ KAr
                 const int ta = t + first;
                 if (tid == 0 && abits_row) atomicOr(abits_row + (ta >> 5), 1u << (ta & 31));
                 if (improved) {
-                    // snapshot: the state at the first visit of the minimum (strict <, :252 / :340); kept in
-                    // shared memory and written out once, when the launch ends
+                    // snapshot: the state at the first visit of the minimum (strict <, :252 / :340).  The copy lives in
+                    // global memory (shared memory is what limits the chains per SM); only the elements moved since
+                    // the previous snapshot are written -- a few bytes, off the critical path
                     best = E;
                     if (!stop) best_step = ta + 1;
-                    snap = true;
                     const int jn = *jcount;
-                    if (jn <= WIDE_JCAP) {
-                        for (int e = tid; e < jn; e += NT) {
-                            const int el = jrn[e];
-                            if constexpr (FULL) store_pos(bst, pos32, el, load_pos(st, pos32, el));
-                            else bst[el] = st[el];
+                    auto put = [&](int el) {
+                        if constexpr (FULL) {
+                            int i, j, k;
+                            unpack_pos(pos32, load_pos(st, pos32, el), i, j, k);
+                            best_out[3 * el] = (uint8_t)i; best_out[3 * el + 1] = (uint8_t)j; best_out[3 * el + 2] = (uint8_t)k;
+                        } else {
+                            best_out[el] = st[el];
                         }
+                    };
+                    if (jn <= WIDE_JCAP) {
+                        for (int e = tid; e < jn; e += NT) put(jrn[e]);
                     } else {
-                        for (int b = tid * 4; b < st_bytes; b += NT * 4)
-                            *reinterpret_cast<uint32_t *>(bst + b) = *reinterpret_cast<const uint32_t *>(st + b);
+                        for (int el = tid; el < a.Q; el += NT) put(el);
                     }
                     jfresh = true;
                 }
@@ -365,18 +374,16 @@ __global__ void __launch_bounds__(NT, 1) wide_kernel(const __grid_constant__ KAr
         a.bin_mark[chain] = bin_mark;
         a.steps_done[chain] = done;
     }
-    for (int pass = 0; pass < 2; ++pass) {
-        if (pass == 1 && !snap) break;
-        const unsigned char *src = pass == 0 ? st : bst;
-        uint8_t *out = (pass == 0 ? a.state : a.best_state) + (size_t)chain * a.state_bytes;
+    {
+        uint8_t *out = a.state + (size_t)chain * a.state_bytes;
         if constexpr (FULL) {
             for (int qi = tid; qi < a.Q; qi += NT) {
                 int i, j, k;
-                unpack_pos(pos32, load_pos(src, pos32, qi), i, j, k);
+                unpack_pos(pos32, load_pos(st, pos32, qi), i, j, k);
                 out[3 * qi] = (uint8_t)i; out[3 * qi + 1] = (uint8_t)j; out[3 * qi + 2] = (uint8_t)k;
             }
         } else {
-            for (int c = tid; c < a.Q; c += NT) out[c] = src[c];
+            for (int c = tid; c < a.Q; c += NT) out[c] = st[c];
         }
     }
 }

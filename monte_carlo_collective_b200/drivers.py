@@ -23,6 +23,7 @@ import numpy as np
 from . import reports
 from . import schedules as _sched
 from .engine import BOARD, FULL, default_engine
+from .multi import default_pool
 
 
 def _mode(mcmc_type):
@@ -43,11 +44,13 @@ def run_beta_start_end_pairs(N, n_steps, beta_start_ends, annealing_type="linear
     mode = _mode(mcmc_type)
     pairs = [(float(a), float(b)) for a, b in beta_start_ends]
     labels = [f"beta: {a}->{b}" for a, b in pairs]
-    tabs = np.stack([_sched.beta_table({"type": annealing_type, "beta_start": a, "beta_end": b}, n_steps) for a, b in pairs])
+    scheds = [_sched.describe(schedule_params={"type": annealing_type, "beta_start": a, "beta_end": b}) for a, b in pairs]
     seeds = np.concatenate([base_seed + idx * 1000 + np.arange(n_runs) for idx in range(len(pairs))]).astype(np.uint64)
     groups = np.repeat(np.arange(len(pairs), dtype=np.int32), n_runs)
-    res = default_engine().run(mode, N, n_steps, seeds, tabs, groups=groups, init_mode=init_mode, history=history,
-                               n_bins=100, early_stop_patience=_patience(mode, early_stop_patience), want_states=False)
+    # one launch per device: every pair is a schedule group (evaluated on the device), chains block-sharded over the GPUs
+    res = default_pool().run(mode, N, n_steps, seeds, schedules=scheds, groups=groups, init_mode=init_mode, history=history,
+                             n_bins=100, early_stop_patience=_patience(mode, early_stop_patience), want_states=False,
+                             stat_count=True)
     out = {"all_histories": {}, "all_best_energies": {}, "mean_energy": {}, "std_energy": {}, "acceptance_rates": {}}
     for idx, label in enumerate(labels):
         sel = slice(idx * n_runs, (idx + 1) * n_runs)
@@ -60,9 +63,11 @@ def run_beta_start_end_pairs(N, n_steps, beta_start_ends, annealing_type="linear
                 arr = np.array(rows, dtype=np.float64)
                 out["mean_energy"][label], out["std_energy"][label] = arr.mean(axis=0), arr.std(axis=0)
         else:
+            # (the count of chains that still have an energy at each index: all of them unless the patience stopped some)
             out["mean_energy"][label], out["std_energy"][label] = reports.mean_std_from_sums(
-                res.stat_sum_e[idx], res.stat_sum_e2[idx], n_runs)
-        centers, rates = reports.acceptance_rates(res.accept_hist[sel].sum(axis=0), n_steps, n_runs)
+                res.stat_sum_e[idx], res.stat_sum_e2[idx], res.stat_count[idx])
+        centers, rates = reports.acceptance_rates(res.accept_hist[sel].sum(axis=0), n_steps, n_runs,
+                                                  steps_done=np.asarray(res.steps_done[sel]))
         out["acceptance_rates"][label] = (centers, rates)
         if verbose:
             for e in best:
@@ -94,43 +99,29 @@ def run_compare_beta_end(Ns, n_steps, beta_start_ends, annealing_type="linear_an
     return {Ns[0]: r1, Ns[1]: r2}
 
 
-_POOL = {}
-
-
-def _pool_engine():
-    """One engine (context + stream) per worker thread, so independent problems overlap on the GPU."""
-    import threading
-    from .engine import Engine
-    tid = threading.get_ident()
-    if tid not in _POOL:
-        _POOL[tid] = Engine(default_engine().device)
-    return _POOL[tid]
-
-
 def measure_min_energy_vs_N(Ns, n_steps, beta_schedule, schedule_params=None, init_modes=["random"], n_runs=5,
                             base_seed=100, verbose=True, plot=True, out_path=None, mcmc_type="full_3d",
                             early_stop_patience=100000, results_dir="results", workers=8):
     """experiments.py:1031-1201: min energy and steps-to-best vs N for each initialisation.
 
-    Every (init_mode, N) point is its own batch of n_runs chains; the points are independent, so they are
-    issued from `workers` host threads (one engine / CUDA stream each) and run concurrently on the GPU."""
-    from concurrent.futures import ThreadPoolExecutor
+    Every (init_mode, N) point is its own batch of n_runs chains with its own geometry; the points are independent,
+    so they are dealt over the visible GPUs and issued from up to `workers` host threads per device (one engine
+    and CUDA stream each, multi.DevicePool.run_many): the launches overlap instead of queueing behind each other."""
     if isinstance(init_modes, str):
         init_modes = [init_modes]
     mode = _mode(mcmc_type)
-    betas = _sched.tabulate(beta_schedule, schedule_params, n_steps)
-
-    def point(job):
-        init_mode, idx, N = job
+    params = _sched.describe(beta_schedule, schedule_params, n_steps)
+    sched_kw = dict(schedules=params) if params is not None else dict(betas=_sched.tabulate(beta_schedule, None, n_steps))
+    keys, jobs = [], []
+    for init_mode in init_modes:
         offset = sum(ord(c) for c in init_mode) % 1000
-        seeds = (base_seed + 10 * idx + offset + np.arange(n_runs)).astype(np.uint64)
-        r = _pool_engine().run(mode, N, n_steps, seeds, betas, init_mode=init_mode, history="none", want_states=False,
-                               early_stop_patience=_patience(mode, early_stop_patience))
-        return np.array(r.best_energy, dtype=np.int64), np.array(r.steps_to_best, dtype=np.int64)
-
-    jobs = [(init_mode, idx, N) for init_mode in init_modes for idx, N in enumerate(Ns)]
-    with ThreadPoolExecutor(max_workers=max(1, workers)) as ex:
-        done = dict(zip(jobs, ex.map(point, jobs)))
+        for idx, N in enumerate(Ns):
+            keys.append((init_mode, idx, N))
+            jobs.append(dict(mcmc_type=mode, n=N, n_steps=n_steps, seeds=(base_seed + 10 * idx + offset + np.arange(n_runs)).astype(np.uint64),
+                             init_mode=init_mode, history="none", want_states=False,
+                             early_stop_patience=_patience(mode, early_stop_patience), **sched_kw))
+    runs = default_pool().run_many(jobs, streams_per_device=max(1, workers))
+    done = {k: (np.array(r.best_energy, dtype=np.int64), np.array(r.steps_to_best, dtype=np.int64)) for k, r in zip(keys, runs)}
     results = {}
     for init_mode in init_modes:
         all_min, all_s2b = [], []
@@ -158,10 +149,9 @@ def competition(N=15, n_runs=10, n_steps=100000, beta_start=1.0, beta_end=3.0, b
                 early_stop_patience=None, out_dir="competition_results", verbose=True, stamp=None):
     """competition.py:143-191: best-of-R board chains, best heights written as `i,j,k` lines.
     n_runs can be thousands here; the file format and the seed rule (base_seed + r) are the reference's."""
-    betas = _sched.beta_table({"type": "linear_annealing", "beta_start": beta_start, "beta_end": beta_end}, n_steps)
     seeds = (base_seed + np.arange(n_runs)).astype(np.uint64)
-    r = default_engine().run(BOARD, N, n_steps, seeds, betas, init_mode=init_mode, history="none",
-                             early_stop_patience=early_stop_patience)
+    r = default_pool().run(BOARD, N, n_steps, seeds, schedules={"type": "linear_annealing", "beta_start": beta_start, "beta_end": beta_end},
+                           init_mode=init_mode, history="none", early_stop_patience=early_stop_patience)
     order = np.argsort(r.best_energy, kind="stable")
     results = [{"run_idx": int(c), "best_energy": int(r.best_energy[c]), "best_state": r.best_state[c].astype(np.int64),
                 "steps_to_best": int(r.steps_to_best[c])} for c in order]
@@ -194,7 +184,7 @@ def parallel_tempering(N, n_steps, betas, n_ladders=64, swap_every=1024, base_se
         raise ValueError("parallel tempering needs at least two temperatures")
     if swap_every % 32 != 0 or swap_every <= 0:
         raise ValueError("swap_every must be a positive multiple of 32")
-    tabs = np.repeat(betas[:, None], n_steps, axis=1)               # constant schedule per rung
+    scheds = [{"type": "constant", "beta_const": float(b)} for b in betas]   # constant schedule per rung
     nc = K * R
     ladder = np.repeat(np.arange(R), K)                             # chain -> ladder
     rung = np.tile(np.arange(K, dtype=np.int32), R)                 # chain -> rung (changes at swaps)
@@ -205,7 +195,7 @@ def parallel_tempering(N, n_steps, betas, n_ladders=64, swap_every=1024, base_se
     means, res, t, seg = [], None, 0, 0
     while t < n_steps or res is None:
         stop = min(n_steps, t + swap_every)
-        res = eng.run(mode, N, n_steps, seeds, tabs, groups=rung.copy(), init_mode=init_mode, history="none",
+        res = eng.run(mode, N, n_steps, seeds, schedules=scheds, groups=rung.copy(), init_mode=init_mode, history="none",
                       resume=res, stop_step=stop if stop < n_steps else None)
         t = stop
         e = np.asarray(res.final_energy, dtype=np.int64)

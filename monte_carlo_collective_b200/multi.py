@@ -48,18 +48,43 @@ def visible_devices():
     return list(range(n.value))
 
 
+#: page-locking gigabytes takes seconds, so released blocks are kept (up to this many bytes) for the next call
+PIN_CACHE_BYTES = 24 << 30
+_pin_cache = {}          # nbytes -> [pointers]
+_pin_cached = 0
+_pin_lock = threading.Lock()
+
+
+def _pin_release(ptr, nbytes):
+    global _pin_cached
+    with _pin_lock:
+        if _pin_cached + nbytes <= PIN_CACHE_BYTES:
+            _pin_cache.setdefault(nbytes, []).append(ptr)
+            _pin_cached += nbytes
+            return
+    _lib.load().mcq_host_free(ptr)
+
+
 def pinned_empty(shape, dtype):
-    """NumPy array on page-locked host memory (cudaHostAlloc through libmcq), freed with the array."""
+    """NumPy array on page-locked host memory (cudaHostAlloc through libmcq).  When the array (and every view of
+    it) is gone the block goes back to a small cache instead of being unlocked."""
+    global _pin_cached
     dtype = np.dtype(dtype)
     nbytes = int(np.prod(shape, dtype=np.int64)) * dtype.itemsize
     if nbytes == 0:
         return np.empty(shape, dtype=dtype)
-    lib = _lib.load()
-    p = C.c_void_p()
-    _lib.check(lib.mcq_host_alloc(C.byref(p), nbytes))
-    buf = (C.c_char * nbytes).from_address(p.value)
+    ptr = None
+    with _pin_lock:
+        if _pin_cache.get(nbytes):
+            ptr = _pin_cache[nbytes].pop()
+            _pin_cached -= nbytes
+    if ptr is None:
+        p = C.c_void_p()
+        _lib.check(_lib.load().mcq_host_alloc(C.byref(p), nbytes))
+        ptr = p.value
+    buf = (C.c_char * nbytes).from_address(ptr)
     arr = np.frombuffer(buf, dtype=dtype).reshape(shape)
-    weakref.finalize(buf, lib.mcq_host_free, p.value)
+    weakref.finalize(buf, _pin_release, ptr, nbytes)
     return arr
 
 

@@ -17,10 +17,15 @@ import pandas as pd
 
 
 def mean_std_from_sums(sum_e, sum_e2, n):
-    """Population mean / std (np.mean, np.std of experiments.py:594-595) from the integer sums."""
-    mean = np.asarray(sum_e, dtype=np.float64) / n
-    var = np.asarray(sum_e2, dtype=np.float64) / n - mean * mean
-    return mean, np.sqrt(np.maximum(var, 0.0))
+    """Population mean / std (np.mean, np.std of experiments.py:594-595) from the integer sums.  ``n``: the number of
+    chains, or -- when the board patience stopped some of them -- the per-step count of chains that still have an
+    energy at that history index (``RunResult.stat_count``); indices no chain reaches come out as NaN."""
+    n = np.asarray(n, dtype=np.float64)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        mean = np.asarray(sum_e, dtype=np.float64) / n
+        var = np.asarray(sum_e2, dtype=np.float64) / n - mean * mean
+        std = np.sqrt(np.maximum(var, 0.0))
+    return (np.where(n > 0, mean, np.nan), np.where(n > 0, std, np.nan)) if n.ndim else (mean, std)
 
 
 def write_energy_csv(label, mean_energy, std_energy, out_dir="results"):
@@ -30,12 +35,20 @@ def write_energy_csv(label, mean_energy, std_energy, out_dir="results"):
     return path
 
 
-def acceptance_rates(accept_counts, n_steps, n_chains, n_bins=100):
-    """(bin_centers, rate per bin) as plot_acceptance_rates_binned computes them (experiments.py:660-700)."""
+def acceptance_rates(accept_counts, n_steps, n_chains, n_bins=100, steps_done=None):
+    """(bin_centers, rate per bin) as plot_acceptance_rates_binned computes them (experiments.py:660-700):
+    accepted / (accepted + rejected) over the steps that were actually executed.  ``steps_done`` (per chain; the
+    history length minus one) matters when the board patience stopped chains early: a stopped chain logged
+    min(steps_done + 1, n_steps) accept / reject decisions, and bins no chain reached are NaN."""
     edges = np.linspace(0, n_steps, n_bins + 1)
     centers = (edges[:-1] + edges[1:]) / 2
-    width = np.diff(np.ceil(edges)).astype(np.float64)
-    total = width * n_chains
+    starts = np.ceil(edges).astype(np.int64)
+    starts[0], starts[-1] = 0, n_steps
+    if steps_done is None:
+        total = np.diff(starts).astype(np.float64) * n_chains
+    else:
+        ran = np.minimum(np.asarray(steps_done, dtype=np.int64) + 1, n_steps)           # decisions logged per chain
+        total = np.clip(ran[None, :] - starts[:-1, None], 0, np.diff(starts)[:, None]).sum(axis=1).astype(np.float64)
     with np.errstate(invalid="ignore", divide="ignore"):
         rates = np.where(total > 0, np.asarray(accept_counts, dtype=np.float64) / total, np.nan)
     return centers, rates

@@ -174,7 +174,8 @@ def run(reference_dir, config_path=None, workdir=None, overrides=(), summary_pat
     if install:
         from . import api
         api.install(mod)
-    mod.plot_energy_histories_side_by_side = _tolerant_side_by_side(mod.plot_energy_histories_side_by_side)
+    if hasattr(mod, "plot_energy_histories_side_by_side"):
+        mod.plot_energy_histories_side_by_side = _tolerant_side_by_side(mod.plot_energy_histories_side_by_side)
     ns = mod.__dict__
     here = os.getcwd()
     os.chdir(workdir)

@@ -73,6 +73,19 @@ def phases(ns, lanes, mode="full_3d", n=12, reps=4096, segs=8):
         emit(dict(what="phases", sched=sp["type"], lanes=lanes, steps=ns, total_ms=round(sum(r["ms"] for r in rows), 2), segs=rows))
 
 
+def wide(n, nc, ns, mode="board", **kw):
+    seeds = torch.arange(nc, dtype=torch.int64).cuda() + 42
+    best = None
+    for _ in range(2):
+        r = eng.run(mode, n, ns, seeds, schedules=SCHEDS[1], history="none", device_buffers=True, want_states=False, **kw)
+        torch.cuda.synchronize()
+        pps = nc * ns / (r.kernel_ms * 1e-3)
+        if best is None or pps > best["pps"]:
+            best = dict(what="wide", mode=mode, n=n, chains=nc, steps=ns, kernel_ms=r.kernel_ms, pps=pps,
+                        acc=float(r.n_accepted.double().mean()) / ns, mean_best=float(r.best_energy.double().mean()), **kw)
+    emit(best)
+
+
 which = sys.argv[1] if len(sys.argv) > 1 else "whole"
 ns = int(float(sys.argv[2])) if len(sys.argv) > 2 else 200000
 if which == "whole":
@@ -80,6 +93,13 @@ if which == "whole":
     whole(ns, history="none")
 elif which == "board":
     whole(ns, mode="board")
+elif which == "wide":
+    for nc, steps in ((148, 100000), (296, 100000), (296, 1000000), (1184, 300000), (4736, 300000), (65536, 100000)):
+        wide(64, nc, steps)
+    wide(30, 2368, 100000)
+    wide(22, 4736, 100000)
+    wide(24, 1184, 100000, mode="full_3d")
+    wide(40, 1184, 100000)
 elif which == "phases":
     for lanes in (32, 16):
         phases(ns, lanes)

@@ -130,3 +130,41 @@ def test_parallel_tempering(mcq, engine):
     cold = engine.run("board", n, ns, (1000 + np.arange(K * R)).astype(np.uint64), np.full((1, ns), betas[-1]), history="none")
     assert pt["best_energy"].min() <= cold.best_energy.min() + 2
     assert np.sort(pt["best_energy"])[: R].mean() < np.sort(cold.best_energy)[: R].mean() + 1.0
+
+
+def test_early_stopped_chains_do_not_bias_means_and_acceptance(mcq):
+    """Board patience stops chains at different steps.  Mean / std curves and binned acceptance rates are taken over
+    the chains that are still running, as the reference's accepted / (accepted + rejected) is
+    (experiments.py:686-693); indices no chain reaches are NaN, not 0."""
+    from monte_carlo_collective_b200 import drivers
+    kw = dict(N=8, n_steps=6000, beta_start_ends=[[1.0, 3.0], [2.0, 6.0]], annealing_type="linear_annealing", n_runs=24,
+              base_seed=3, verbose=False, plot=False, mcmc_type="board", early_stop_patience=150)
+    full = drivers.run_beta_start_end_pairs(history="full", **kw)
+    st = drivers.run_beta_start_end_pairs(history="stats", **kw)
+    for idx, label in enumerate(full["all_histories"]):
+        rows = full["all_histories"][label]
+        lens = np.array([len(r) for r in rows])
+        assert lens.min() < 6001, "the patience must actually stop chains in this test"
+        want_mean = np.full(6001, np.nan)
+        want_std = np.full(6001, np.nan)
+        for h in range(6001):
+            v = np.array([r[h] for r in rows if len(r) > h], dtype=np.float64)
+            if len(v):
+                want_mean[h], want_std[h] = v.mean(), v.std()
+        assert np.allclose(st["mean_energy"][label], want_mean, equal_nan=True)
+        assert np.allclose(st["std_energy"][label], want_std, equal_nan=True, atol=1e-9)
+        # acceptance: accepted / logged decisions per bin, from per-chain histories
+        centers, rates = st["acceptance_rates"][label]
+        edges = np.ceil(np.linspace(0, 6000, 101)).astype(int)
+        acc = np.zeros(100)
+        tot = np.zeros(100)
+        for r in rows:
+            ran = min(len(r), 6000)                       # a stopped chain logged its stopping step, too
+            for b in range(100):
+                lo, hi = edges[b], min(edges[b + 1], ran)
+                if hi > lo:
+                    tot[b] += hi - lo
+        got_counts = rates * tot
+        assert np.all(np.isnan(rates[tot == 0])) and np.all(np.isfinite(rates[tot > 0]))
+        assert np.allclose(got_counts[tot > 0], np.round(got_counts[tot > 0]))       # integer accept counts over that denominator
+        assert np.allclose(np.asarray(full["acceptance_rates"][label][1])[tot > 0], rates[tot > 0])
