@@ -194,7 +194,10 @@ __global__ void __launch_bounds__(NT, 1) wide_kernel(const __grid_constant__ KAr
                 constexpr int f = decltype(fc)::value;
                 if constexpr (f >= F0) {
                     io[f] = line_index_f<f>(a, i0, j0, k0c);
-                    in[f] = line_index_f<f>(a, i1, j1, k1c);
+                    // a board move changes k only: the new cell's line of a family is the old one's shifted along k
+                    // (the fold of the space-diagonal families depends on i and j alone)
+                    if constexpr (FULL) in[f] = line_index_f<f>(a, i1, j1, k1c);
+                    else in[f] = io[f] + a.coef[f].z * (k1c - k0c);
                 }
             };
             both(std::integral_constant<int, 0>{}); both(std::integral_constant<int, 1>{}); both(std::integral_constant<int, 2>{});

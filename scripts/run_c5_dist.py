@@ -40,13 +40,13 @@ def main():
 
     eng = mcq.Engine(local)
     lo, hi = shard_bounds(args.chains, rank, world)
-    betas = schedules.beta_table({"type": "linear_annealing", "beta_start": 1.0, "beta_end": 3.0}, args.steps)
+    sched = {"type": "linear_annealing", "beta_start": 1.0, "beta_end": 3.0}
     seeds = np.arange(lo, hi, dtype=np.uint64)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     t0 = time.time()
-    r = eng.run("board", args.n, args.steps, seeds, betas, history="none", want_states=False, chunk_steps=500000)
+    r = eng.run("board", args.n, args.steps, seeds, schedules=sched, history="none", want_states=False)
     red = reduce_results(r.best_energy, r.n_accepted, lo, device=torch.device(f"cuda:{local}"))
     sums = torch.tensor([float(r.best_energy.sum()), float(r.final_energy.sum()), r.kernel_ms], dtype=torch.float64, device=f"cuda:{local}")
     mx = sums[2:].clone()

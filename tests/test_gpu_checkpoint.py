@@ -72,3 +72,26 @@ def test_resume_argument_errors(engine):
         engine.run("board", 6, ns, seeds, betas, resume=a, stop_step=32)   # stop before start
     b = engine.run("board", 6, ns, seeds, betas, resume=a, stop_step=64)   # empty segment
     assert (b.final_state == a.final_state).all() and (b.record == a.record).all()
+
+
+@pytest.mark.parametrize("mode,n", [("full_3d", 12), ("board", 12), ("board", 24)])
+def test_statistics_survive_a_file_checkpoint(engine, mode, n, tmp_path):
+    """A statistics run resumed from a FILE continues the sums of the earlier segments: the checkpoint carries the
+    cumulative outputs, and a resumed run never continues into uninitialised arrays."""
+    ns, nc = 1024, 20
+    seeds = np.arange(nc, dtype=np.uint64) + 5
+    kw = dict(schedules=LIN, history="stats", n_bins=16, stat_count=True)
+    whole = engine.run(mode, n, ns, seeds, **kw)
+    a = engine.run(mode, n, ns, seeds, stop_step=384, **kw)
+    a.save_checkpoint(tmp_path / "ck.npz")
+    ck = mcq.load_checkpoint(tmp_path / "ck.npz")
+    assert ck.stat_sum_e is not None and ck.accept_hist is not None
+    b = engine.run(mode, n, ns, seeds, resume=ck, **kw)
+    for name in ("stat_sum_e", "stat_sum_e2", "stat_count", "accept_hist", "best_energy", "final_energy", "n_accepted", "final_state"):
+        assert (np.asarray(getattr(b, name)) == np.asarray(getattr(whole, name))).all(), name
+    # a checkpoint without the cumulative arrays (older file / want them dropped): the resumed run starts them from zero
+    # for the columns it executes -- defined values, the earlier columns are simply absent
+    ck.stat_sum_e = ck.stat_sum_e2 = ck.stat_count = ck.accept_hist = None
+    c = engine.run(mode, n, ns, seeds, resume=ck, **kw)
+    assert (np.asarray(c.stat_sum_e)[:, :385] == 0).all()
+    assert (np.asarray(c.final_state) == np.asarray(whole.final_state)).all()
