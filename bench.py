@@ -18,7 +18,7 @@ best / final energy, steps-to-best, accept counts, 100-bin acceptance histograms
            through the drop-in API: full uint16 histories and accept bitmaps of every chain come back to the host.
   N>1      one process per GPU (torchrun); replicas are sharded (each GPU runs its own replicas: weak scaling), no
            data-path collective; per-schedule statistics and the global best energy are reduced with NCCL inside
-           the timed step (`--segments k` reduces segment by segment under the kernels of the next segment).
+           the timed step (one 80 MB all_reduce of copies of the statistics + two scalars per pass).
 
 `--impl reference` times the reference's CPU algorithm (oracle/queens_numpy.py, a NumPy restatement pinned to the
 reference by tests/golden; the reference itself is pure Python and does not exist on the GPU box) on all host
@@ -223,9 +223,6 @@ def main():
     ap.add_argument("--replicas", type=int, default=0, help="replicas per schedule per GPU (default: the workload's)")
     ap.add_argument("--chain-steps", type=int, default=0, help="proposals per chain per pass (default: the workload's)")
     ap.add_argument("--cpu-steps", type=int, default=20000, help="proposals per chain in the CPU sample")
-    ap.add_argument("--segments", type=int, default=0,
-                    help="segments per pass; with N>1 the statistics of a finished segment are reduced under the next segment's kernels "
-                         "(default 1: measured, a segment boundary costs about what the overlap saves)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-api-e2e", action="store_true")
@@ -264,8 +261,6 @@ def main():
     ns, reps, ng = args.chain_steps, args.replicas, len(scheds)
     nc = reps * ng
     dev = torch.device(f"cuda:{local}")
-    n_seg = args.segments or 1
-    bounds = [min(ns, (ns * k // n_seg) // 32 * 32) for k in range(n_seg)] + [ns]
 
     # ---- synthetic inputs ----
     seeds_h = chain_seeds(args.workload, rank, reps)
@@ -274,50 +269,31 @@ def main():
     groups_d = torch.from_numpy(groups_h).to(dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream()
-    if os.environ.get("MCQ_BENCH_SIDESTREAM"):
-        stream = torch.cuda.Stream(device=dev)
-        torch.cuda.set_stream(stream)
     out_d = {}
     comm = torch.zeros((2, ng, ns + 1), dtype=torch.int64, device=dev) if world > 1 else None   # job-wide sum E, sum E^2
     keep = ("stat_sum_e", "stat_sum_e2", "best_energy", "final_energy", "steps_to_best", "n_accepted", "steps_done",
             "initial_energy", "final_state", "best_state", "accept_hist", "n_near_threshold", "n_fp32_flips", "record")
 
     def device_pass():
-        """One pass = n_seg segments of the schedule.  With N>1 the statistics columns of a finished segment are
-        all-reduced (NCCL, asynchronous) while the next segment's kernels run; the last segment's reduction and the
-        scalar reductions are the only communication left exposed."""
-        r, works, ms, launches, near, flips = None, [], 0.0, 0, 0, 0
-        for k in range(n_seg):
-            stop = bounds[k + 1]
-            r = eng.run(mode, n, ns, seeds_d, schedules=scheds, groups=groups_d, history="stats", n_bins=100, device_buffers=True,
-                        stream=stream.cuda_stream, out=out_d, resume=r, stop_step=stop if stop < ns else None)
-            ms += r.kernel_ms
-            launches += r.gpu_launches
-            near = near + r.n_near_threshold.sum(dtype=torch.int64)      # (per-segment counters)
-            flips = flips + r.n_fp32_flips.sum(dtype=torch.int64)
-            for name in keep:
-                out_d[name] = getattr(r, name)
-            if world > 1 and not os.environ.get("MCQ_BENCH_NOREDUCE"):
-                # The reduction runs on COPIES: the arrays the kernels add into with device atomics stay private to
-                # this GPU (NCCL may register / multicast-map the buffers it is handed on an NVSwitch box; the chain
-                # kernel was measured 9 % slower after its statistics arrays had been all-reduced in place).
-                lo = 0 if k == 0 else bounds[k] + 1
-                comm[0, :, lo:stop + 1].copy_(r.stat_sum_e[:, lo:stop + 1])
-                comm[1, :, lo:stop + 1].copy_(r.stat_sum_e2[:, lo:stop + 1])
-                if n_seg == 1:
-                    dist.all_reduce(comm, op=dist.ReduceOp.SUM)          # one 80 MB collective per pass
-                else:                                                     # column slices are not contiguous: row by row
-                    for a_ in range(2):
-                        for g in range(ng):
-                            works.append(dist.all_reduce(comm[a_, g, lo:stop + 1], op=dist.ReduceOp.SUM, async_op=True))
-        if world > 1 and not os.environ.get("MCQ_BENCH_NOREDUCE"):   # the only exchange of the path: final reductions over NCCL
+        """One pass: the whole anneal of this rank's chains (one chain-kernel launch), then -- with N > 1 -- the only
+        exchange of the path, one NCCL step: sum E / sum E^2 of every schedule and step (one 80 MB all_reduce), the
+        global best energy and the accept count."""
+        r = eng.run(mode, n, ns, seeds_d, schedules=scheds, groups=groups_d, history="stats", n_bins=100, device_buffers=True,
+                    stream=stream.cuda_stream, out=out_d)
+        for name in keep:
+            out_d[name] = getattr(r, name)
+        if world > 1:
+            # The reduction runs on a COPY, as ONE contiguous synchronous collective.  (Measured on an 8-GPU NVSwitch
+            # box: reducing the kernels' own arrays in place, or row by row with async_op=True, left the chain kernel of
+            # the next pass 9-13 % slower on some ranks -- scaling efficiency 0.89; this form gives 0.997.)
+            comm[0].copy_(r.stat_sum_e)
+            comm[1].copy_(r.stat_sum_e2)
+            dist.all_reduce(comm, op=dist.ReduceOp.SUM)
             gmin = r.best_energy.min().reshape(1)
             dist.all_reduce(gmin, op=dist.ReduceOp.MIN)
             acc = r.n_accepted.sum(dtype=torch.int64).reshape(1)
             dist.all_reduce(acc, op=dist.ReduceOp.SUM)
-            for w in works:
-                w.wait()
-        r.kernel_ms, r.gpu_launches, r.band = ms, launches, torch.stack([near, flips])
+        r.band = torch.stack([r.n_near_threshold.sum(dtype=torch.int64), r.n_fp32_flips.sum(dtype=torch.int64)])
         return r
 
     def sync_all():
@@ -467,7 +443,6 @@ def main():
             "min_energy_reached": best_min, "acceptance_rate": acc_rate,
             "accept_band": {"decisions_in_float64": int(band[0].item()), "float32_would_have_flipped": int(band[1].item()),
                             "proposals": nc * ns * world},
-            "segments_per_pass": n_seg,
             "metric_full": "MCMC proposals/sec (N=12, 1/2/4/8 B200) vs host-CPU ref; min energy reached",
         }
         emit(line)

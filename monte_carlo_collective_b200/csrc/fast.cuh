@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(LPC == 32 ? 32 * MCQ_FAST_WARPS : 128, LPC == 
 
     for (;;) {
         // ---------------- spans: close the bins that end here, open the next span, or leave ----------------
-        if (CPW == 1 ? t >= span_end : __any_sync(FULLMASK, t >= span_end)) {
+        {
             if (t >= span_end && t < a.t_end) {
                 int bin = (int)SM32(sR + 4).get(), bin_mark = (int)SM32(sR + 8).get();
                 int edge = a.bin_starts[bin + 1];
@@ -157,6 +157,8 @@ __global__ void __launch_bounds__(LPC == 32 ? 32 * MCQ_FAST_WARPS : 128, LPC == 
             }
             if (CPW == 1 ? t >= a.t_end : __all_sync(FULLMASK, t >= a.t_end)) break;
         }
+        // ---------------- the rounds of this span: the loop condition is the only per-round edge test ----------------
+        do {
         const int s = t + sub;                    // lanes past the end of the span evaluate too; they are masked below
         const bool valid = s < span_end;          // (a finished chain of a two-chain warp has no valid lane)
 
@@ -323,6 +325,7 @@ __global__ void __launch_bounds__(LPC == 32 ? 32 * MCQ_FAST_WARPS : 128, LPC == 
             if (sub == 0 && a.flip_cnt && (flipm & committed)) atomicAdd(a.flip_cnt + chain, (unsigned)__popc(flipm & committed));
         }
         t += adv;
+        } while (CPW == 1 ? t < span_end : __all_sync(FULLMASK, t < span_end));
     }
 
     // ---------------- write the record back ----------------
