@@ -136,7 +136,9 @@ __global__ void __launch_bounds__(LPC == 32 ? 32 * MCQ_FAST_WARPS : 128, LPC == 
     if (!live) span_end = a.t_end;
     const int sG = sT + sl.off_ring;
     int tfill = t;
-    [[maybe_unused]] const uint32_t srow = HK == 3 ? (uint32_t)grp * (uint32_t)a.stat_pitch : 0u;
+    // statistics row of this chain's group (sum E; the sum E^2 row sits at a fixed distance)
+    [[maybe_unused]] unsigned long long *srow_e = HK == 3 ? a.dsum_e + (size_t)grp * (size_t)a.stat_pitch : nullptr;
+    [[maybe_unused]] const long long s2_off = HK == 3 ? (long long)(a.dsum_e2 - a.dsum_e) : 0;
     [[maybe_unused]] unsigned char *hrow = static_cast<unsigned char *>(a.hist) + ((long long)chain_c * a.hist_pitch - a.h_origin) * 2;
     const bool want_abits = a.abits != nullptr;
 
@@ -164,7 +166,7 @@ __global__ void __launch_bounds__(LPC == 32 ? 32 * MCQ_FAST_WARPS : 128, LPC == 
 
         // ---------------- this lane's proposal: step s against the current state ----------------
         const float cb = __ldg(ptr_mad(beta_row, (uint32_t)s, 4u));
-        if (tfill < t + LPC && t < a.t_end) {
+        if (tfill < t + LPC && (CPW == 1 || t < a.t_end)) {   // (one chain per warp: t < span_end <= t_end inside this loop)
             const Philox4 w = chain_words((uint32_t)(tfill + sub), key0, key1, PHILOX_STREAM_STEP);
             asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(sbase + (uint32_t)(sG + 16 * ((tfill + sub) & (RING - 1)))),
                          "r"(w.x), "r"(w.y), "r"(w.z), "r"(w.w) : "memory");
@@ -174,7 +176,7 @@ __global__ void __launch_bounds__(LPC == 32 ? 32 * MCQ_FAST_WARPS : 128, LPC == 
         Philox4 r;
         asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
                      : "r"(sbase + (uint32_t)(sG + 16 * (s & (RING - 1)))));
-        uint32_t c0, c1, aux;
+        uint32_t c0, c1, aux_lo, aux_hi;   // what the commit needs besides the two cells: packed only in rounds that commit
         int dE;
         if (FULL) {
             const uint32_t N3 = (uint32_t)(N * N * N);
@@ -205,7 +207,7 @@ __global__ void __launch_bounds__(LPC == 32 ? 32 * MCQ_FAST_WARPS : 128, LPC == 
 #else
             dE = (v1 & CNT) - ((int)(TE)TBL(sT, c0) & CNT) + 1 - (int)((SM32(4 * (e >> 5)) >> (e & 31)) & 1u);
 #endif
-            aux = q | (w1 << 16);
+            aux_lo = q; aux_hi = w1;
         } else {
             const uint32_t ij = __umulhi(r.x, (uint32_t)(N * N));
             const uint32_t k0 = SM8(sP + ij);
@@ -213,7 +215,7 @@ __global__ void __launch_bounds__(LPC == 32 ? 32 * MCQ_FAST_WARPS : 128, LPC == 
             k1 -= (k1 >= (uint32_t)N) ? (uint32_t)N : 0u;
             c0 = ij * N + k0; c1 = ij * N + k1;
             dE = (int)(TE)TBL(sT, c1) - (int)(TE)TBL(sT, c0) + 1;
-            aux = ij | (k1 << 16);
+            aux_lo = ij; aux_hi = k1;
         }
         bool accept, near_band;
         metropolis_fast(dE, cb, r.z, a.band_abs, accept, near_band);
@@ -251,7 +253,7 @@ __global__ void __launch_bounds__(LPC == 32 ? 32 * MCQ_FAST_WARPS : 128, LPC == 
         const int src = half * LPC + max(first, 0);
         const int wdE = __shfl_sync(FULLMASK, dE, src);
         const uint32_t wc0 = __shfl_sync(FULLMASK, c0, src), wc1 = __shfl_sync(FULLMASK, c1, src);
-        const uint32_t waux = __shfl_sync(FULLMASK, aux, src);
+        const uint32_t waux = __shfl_sync(FULLMASK, aux_lo | (aux_hi << 16), src);
         const int E_new = has ? E + wdE : E;
         if (HK == 1 && sub < adv) *reinterpret_cast<uint16_t *>(ptr_mad(hrow + 2, (uint32_t)s, 2u)) = (uint16_t)((sub == first) ? E_new : E);
         // ---------------- apply the committed moves: whole warp, one chain after the other ----------------
@@ -297,9 +299,9 @@ __global__ void __launch_bounds__(LPC == 32 ? 32 * MCQ_FAST_WARPS : 128, LPC == 
             if (HK == 3 && sub == 0 && E_new != E) {
                 // sum E / sum E^2 over the replicas of a group, difference form (KArgs::dsum_e)
                 const long long de = (long long)(E_new - E);
-                unsigned long long *pe = a.dsum_e + (srow + (uint32_t)(ta + 1));
+                unsigned long long *pe = srow_e + (ta + 1);
                 atomicAdd(pe, (unsigned long long)de);
-                atomicAdd(pe + (a.dsum_e2 - a.dsum_e), (unsigned long long)(de * (long long)(E_new + E)));
+                atomicAdd(pe + s2_off, (unsigned long long)(de * (long long)(E_new + E)));
             }
             E = E_new;
             ++n_acc;
