@@ -686,21 +686,26 @@ int mcq_run(mcq_ctx *ctx, const mcq_run_params *p) {
         while (G < 32 && (size_t)make_layout(full, p->n, p->q, G).stride * (32 / G) > smem_block) G *= 2;
     }
     Layout lay = make_layout(full, p->n, p->q, G);
-    // CTA-per-chain kernel: 8, 4, 2 or 1 warps per chain.  A round is bound by its dependent instruction chain, so what
-    // counts is how many chains an SM holds (shared memory: counters + state + a ring of 2 * threads steps;
-    // registers: 128 per thread); among equals the widest CTA speculates furthest.  warps_per_cta = 1, 2, 4, 8 overrides.
+    // CTA-per-chain kernel: 8, 4, 2 or 1 warps per chain.  What counts first is how many chains an SM holds (shared
+    // memory: counters + state + a ring of 2 * threads steps; registers: 128 per thread).  Among the widths that
+    // reach that residency: one warp up to N = 40 (no block barrier at all), two warps beyond (measured, round 2:
+    // N = 22..40 run 8-25 % faster on one warp than on two; N = 48 and 64 are 4-10 % faster on two warps than on
+    // one or four).  warps_per_cta = 1, 2, 4, 8 overrides.
     const int w_best = lay.off_pkt, w_ring = lay.off_pkt;   // (the best state is kept in global memory: no shared copy)
     int wide_threads = WIDE_THREADS;
     auto wide_bytes = [&](int nt) { return (size_t)w_ring + 2 * (size_t)nt * 16 + WIDE_XCH_BYTES; };
     if (use_wide) {
         const long long want = (nc + ctx->prop.multiProcessorCount - 1) / ctx->prop.multiProcessorCount;   // chains per SM on offer
         long long best_conc = 0;
-        for (int nt = 256; nt >= 32; nt >>= 1) {
-            if (wide_bytes(nt) > smem_block) continue;
+        const int preferred = p->n <= 40 ? 32 : 64;
+        auto residency = [&](int nt) -> long long {
+            if (wide_bytes(nt) > smem_block) return 0;
             const long long by_smem = (long long)(smem_sm / (wide_bytes(nt) + 1024)), by_regs = 65536 / (128 * nt);
-            const long long conc = std::min(want, std::min<long long>(32, std::min(by_smem, by_regs)));
-            if (conc > best_conc) { best_conc = conc; wide_threads = nt; }
-        }
+            return std::min(want, std::min<long long>(32, std::min(by_smem, by_regs)));
+        };
+        for (int nt = 32; nt <= 256; nt <<= 1) best_conc = std::max(best_conc, residency(nt));   // (non-increasing in nt)
+        for (int nt = 32; nt <= preferred; nt <<= 1)
+            if (residency(nt) == best_conc) wide_threads = nt;                                    // the widest up to the preferred one
         if (best_conc == 0) return fail(MCQ_ENOMEM, "the line counters of one chain do not fit in shared memory");
         if (p->warps_per_cta == 1 || p->warps_per_cta == 2 || p->warps_per_cta == 4 || p->warps_per_cta == 8) wide_threads = p->warps_per_cta * 32;
         if (const char *e = getenv("MCQ_WIDE_THREADS")) { const int v = atoi(e); if (v == 32 || v == 64 || v == 128 || v == 256) wide_threads = v; }
