@@ -18,6 +18,8 @@
  *                          for known-answer tests; the reference uses NumPy's MT19937)
  *   mcq_philox4x32_10_device -- the same generator as compiled for the GPU (known-answer tests
  *                          of the device code itself)
+ *   mcq_philox2x32_10, mcq_philox2x32_10_device -- the two-word generator of the same family that
+ *                          board steps draw from (a board step needs 64 random bits)
  *   mcq_beta_table      <- constant_beta / linear / exponential / logarithmic / sinusoidal
  *                          annealing schedules, experiments.py:13-77, evaluated on the device
  *
@@ -37,7 +39,7 @@
 extern "C" {
 #endif
 
-#define MCQ_ABI_VERSION 3
+#define MCQ_ABI_VERSION 4
 #define MCQ_RECORD_INTS 8
 
 /* state space (experiments.py:497-502: "board" or anything else => full_3d) */
@@ -109,7 +111,7 @@ typedef struct mcq_run_params {
     int32_t early_stop_patience; /* board only (experiments.py:349-353); < 0 = none */
 
     /* ---- inputs ---- */
-    const uint64_t *chain_seeds; /* [n_chains] Philox key; depends on the chain only, never on placement */
+    const uint64_t *chain_seeds; /* [n_chains] Philox seed; depends on the chain only, never on placement */
     const int32_t *chain_group;  /* [n_chains] in [0,n_groups), or NULL = all 0 */
     const mcq_schedule *schedules; /* [n_groups] schedule parameters: beta_t is evaluated on the device (production path;
                                       HOST memory always), or NULL when beta_f64 carries a tabulated schedule */
@@ -222,6 +224,11 @@ int mcq_host_free(void *ptr);
 void mcq_philox4x32_10(const uint32_t counter[4], const uint32_t key[2], uint32_t out[4]);
 /* the device build of the same function: n calls, counters [n][4], keys [n][2], out [n][4] (HOST pointers) */
 int mcq_philox4x32_10_device(mcq_ctx *ctx, int n, const uint32_t *counters, const uint32_t *keys, uint32_t *out);
+/* Philox2x32-10, host and device builds: the words of board step s of a chain are
+ * philox2x32_10(counter = (s, seed_lo), key = 0x243F6A88 ^ seed_hi).  Device form: counters [n][2], keys [n], out [n][2];
+ * a key of 0x243F6A88 takes the compiled-constant path the kernels use for seeds below 2^32. */
+void mcq_philox2x32_10(const uint32_t counter[2], uint32_t key, uint32_t out[2]);
+int mcq_philox2x32_10_device(mcq_ctx *ctx, int n, const uint32_t *counters, const uint32_t *keys, uint32_t *out);
 
 /* beta(step) of `n_groups` schedules evaluated on the device: out_beta[g][s] float64 (the value the float64 accept
  * rule uses), out_c[g][s] float32(-beta log2 e) (what the float32 fast path reads); either may be NULL.  HOST pointers. */

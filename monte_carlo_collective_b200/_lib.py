@@ -17,7 +17,7 @@ INIT_RANDOM, INIT_LATIN, INIT_KLARNER, INIT_EXPLICIT = 0, 1, 2, 3
 MEM_HOST, MEM_DEVICE = 0, 1
 HIST_NONE, HIST_U16, HIST_I32 = 0, 1, 2
 OK, EINVAL, ECUDA, ENOMEM, EREPLAY = 0, -1, -2, -3, -4
-ABI_VERSION = 3
+ABI_VERSION = 4
 ALGO_AUTO, ALGO_LINES, ALGO_TABLE, ALGO_GMEM, ALGO_WIDE = 0, 1, 2, 3, 4
 SCHED_CONSTANT, SCHED_LINEAR, SCHED_EXPONENTIAL, SCHED_LOGARITHMIC, SCHED_SINUSOIDAL = 0, 1, 2, 3, 4
 
@@ -114,6 +114,8 @@ SYMBOLS = [
     ("mcq_host_free", C.c_int, [C.c_void_p]),
     ("mcq_philox4x32_10", None, [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     ("mcq_philox4x32_10_device", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("mcq_philox2x32_10", None, [C.POINTER(C.c_uint32), C.c_uint32, C.POINTER(C.c_uint32)]),
+    ("mcq_philox2x32_10_device", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("mcq_beta_table", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
 ]
 

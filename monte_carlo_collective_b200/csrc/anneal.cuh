@@ -385,7 +385,7 @@ __global__ void __launch_bounds__(G == 1 ? 128 : 256, G == 1 ? 3 : 1) anneal_ker
                 w1 = make_uint4(mv_row[ts], (uint32_t)__double2loint(u), (uint32_t)__double2hiint(u), (uint32_t)__double2loint(b));
                 w1_4 = (uint32_t)__double2hiint(b);
             } else {
-                const Philox4 r = chain_words((uint32_t)ts, k0, k1, PHILOX_STREAM_STEP);
+                const Philox4 r = step_words<FULL>((uint32_t)ts, k0, k1, (uint32_t)(N * N));
                 w1 = make_uint4(r.x, r.y, r.z, r.w);
                 w1_4 = __float_as_uint(c_pref);                       // fetched one step ahead
                 if (live && ts + 1 < a.t_end) c_pref = __ldg(beta_row + ts + 1);
@@ -402,7 +402,7 @@ __global__ void __launch_bounds__(G == 1 ? 128 : 256, G == 1 ? 3 : 1) anneal_ker
                         p[1] = (uint32_t)__double2loint(u); p[2] = (uint32_t)__double2hiint(u);
                         p[3] = (uint32_t)__double2loint(b); p[4] = (uint32_t)__double2hiint(b);
                     } else {
-                        const Philox4 r = chain_words((uint32_t)ts, k0, k1, PHILOX_STREAM_STEP);
+                        const Philox4 r = step_words<FULL>((uint32_t)ts, k0, k1, (uint32_t)(N * N));
                         *reinterpret_cast<uint4 *>(p) = make_uint4(r.x, r.y, r.z, r.w);
                         p[4] = __float_as_uint(c_pref);
                         const int tn = ts + PB;

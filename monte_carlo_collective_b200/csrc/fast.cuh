@@ -167,15 +167,27 @@ __global__ void __launch_bounds__(LPC == 32 ? 32 * MCQ_FAST_WARPS : 128, LPC == 
         // ---------------- this lane's proposal: step s against the current state ----------------
         const float cb = __ldg(ptr_mad(beta_row, (uint32_t)s, 4u));
         if (tfill < t + LPC && (CPW == 1 || t < a.t_end)) {   // (one chain per warp: t < span_end <= t_end inside this loop)
-            const Philox4 w = chain_words((uint32_t)(tfill + sub), key0, key1, PHILOX_STREAM_STEP);
-            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(sbase + (uint32_t)(sG + 16 * ((tfill + sub) & (RING - 1)))),
-                         "r"(w.x), "r"(w.y), "r"(w.z), "r"(w.w) : "memory");
+            if (FULL) {
+                const Philox4 w = chain_words((uint32_t)(tfill + sub), key0, key1, PHILOX_STREAM_STEP);
+                asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(sbase + (uint32_t)(sG + 16 * ((tfill + sub) & (RING - 1)))),
+                             "r"(w.x), "r"(w.y), "r"(w.z), "r"(w.w) : "memory");
+            } else {   // a board step needs two words: Philox2x32-10, eight bytes of the ring
+#ifdef MCQ_DBG_BOARD_PHILOX4   // sensitivity probe only (not a product configuration): the cost of the four-word generator
+                const Philox4 w4 = chain_words((uint32_t)(tfill + sub), key0, key1, PHILOX_STREAM_STEP);
+                Philox2 w; w.x = w4.x ^ w4.y; w.z = w4.z ^ w4.w;
+#else
+                const Philox2 w = board_step_words((uint32_t)(tfill + sub), key0, key1);
+#endif
+                asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(sbase + (uint32_t)(sG + 8 * ((tfill + sub) & (RING - 1)))),
+                             "r"(w.x), "r"(w.z) : "memory");
+            }
             tfill += LPC;
         }
         __syncwarp();
         Philox4 r;
-        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
-                     : "r"(sbase + (uint32_t)(sG + 16 * (s & (RING - 1)))));
+        if (FULL) asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                               : "r"(sbase + (uint32_t)(sG + 16 * (s & (RING - 1)))));
+        else asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.z) : "r"(sbase + (uint32_t)(sG + 8 * (s & (RING - 1)))));
         uint32_t c0, c1, aux_lo, aux_hi;   // what the commit needs besides the two cells: packed only in rounds that commit
         int dE;
         if (FULL) {
@@ -209,9 +221,10 @@ __global__ void __launch_bounds__(LPC == 32 ? 32 * MCQ_FAST_WARPS : 128, LPC == 
 #endif
             aux_lo = q; aux_hi = w1;
         } else {
-            const uint32_t ij = __umulhi(r.x, (uint32_t)(N * N));
+            const unsigned long long col = (unsigned long long)r.x * (uint32_t)(N * N);   // column digit, then the height offset
+            const uint32_t ij = (uint32_t)(col >> 32);
             const uint32_t k0 = SM8(sP + ij);
-            uint32_t k1 = k0 + 1u + __umulhi(r.y, (uint32_t)(N - 1));
+            uint32_t k1 = k0 + 1u + __umulhi((uint32_t)col, (uint32_t)(N - 1));
             k1 -= (k1 >= (uint32_t)N) ? (uint32_t)N : 0u;
             c0 = ij * N + k0; c1 = ij * N + k1;
             dE = (int)(TE)TBL(sT, c1) - (int)(TE)TBL(sT, c0) + 1;

@@ -307,6 +307,14 @@ __global__ void philox_kat_kernel(int n, const uint32_t *ctr, const uint32_t *ke
     out[4 * i] = r.x; out[4 * i + 1] = r.y; out[4 * i + 2] = r.z; out[4 * i + 3] = r.w;
 }
 
+__global__ void philox2_kat_kernel(int n, const uint32_t *ctr, const uint32_t *key, uint32_t *out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    // through board_step_words, so that both compiled forms (constant key / key in a register) are the ones tested
+    const Philox2 r = board_step_words(ctr[2 * i], ctr[2 * i + 1], key[i] ^ CHAIN_KEY0);
+    out[2 * i] = r.x; out[2 * i + 1] = r.z;
+}
+
 // float64 beta(step) of parametrised schedules (what metropolis_exact evaluates on demand)
 __global__ void beta64_table_kernel(const SchedDev *sched, int n_groups, int n_steps, double *out) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -512,6 +520,28 @@ int mcq_philox4x32_10_device(mcq_ctx *ctx, int n, const uint32_t *counters, cons
                                                       static_cast<const uint32_t *>(ctx->buf[B_SEEDS].p), static_cast<uint32_t *>(ctx->buf[B_OUT].p));
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpyAsync(out, ctx->buf[B_OUT].p, (size_t)n * 16, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return 0;
+}
+
+void mcq_philox2x32_10(const uint32_t counter[2], uint32_t key, uint32_t out[2]) {
+    const Philox2 r = philox2x32_10(counter[0], counter[1], key);
+    out[0] = r.x; out[1] = r.z;
+}
+
+int mcq_philox2x32_10_device(mcq_ctx *ctx, int n, const uint32_t *counters, const uint32_t *keys, uint32_t *out) {
+    if (!ctx || n < 0 || (n && (!counters || !keys || !out))) return fail(MCQ_EINVAL, "bad arguments");
+    if (n == 0) return 0;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    if (ctx->buf[B_MOVES].ensure((size_t)n * 8) || ctx->buf[B_OUT].ensure((size_t)n * 8) || ctx->buf[B_SEEDS].ensure((size_t)n * 4))
+        return fail(MCQ_ENOMEM, "device allocation failed");
+    CUDA_TRY(cudaMemcpyAsync(ctx->buf[B_MOVES].p, counters, (size_t)n * 8, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(ctx->buf[B_SEEDS].p, keys, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+    philox2_kat_kernel<<<(n + 127) / 128, 128, 0, s>>>(n, static_cast<const uint32_t *>(ctx->buf[B_MOVES].p),
+                                                       static_cast<const uint32_t *>(ctx->buf[B_SEEDS].p), static_cast<uint32_t *>(ctx->buf[B_OUT].p));
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(out, ctx->buf[B_OUT].p, (size_t)n * 8, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
     return 0;
 }

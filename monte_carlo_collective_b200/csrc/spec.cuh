@@ -318,7 +318,7 @@ __global__ void __launch_bounds__(128, LPC == 32 ? MCQ_SPEC_MINB : 5) spec_kerne
             // steps it commits, so one Philox4x32-10 call per lane refills LPC steps that are all used,
             // instead of recomputing the discarded lanes' words every round.
             if (active && tfill < t + LPC) {
-                const Philox4 w = chain_words((uint32_t)(tfill + sub), key0, key1, PHILOX_STREAM_STEP);
+                const Philox4 w = step_words<FULL>((uint32_t)(tfill + sub), key0, key1, (uint32_t)(N * N));
                 asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(sbase + (uint32_t)(sG + 16 * ((tfill + sub) & 63))),
                              "r"(w.x), "r"(w.y), "r"(w.z), "r"(w.w) : "memory");
                 tfill += LPC;

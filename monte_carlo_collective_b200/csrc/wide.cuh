@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(NT, 1) wide_kernel(const __grid_constant__ KAr
     while (t < a.t_end) {
         // ---------------- random words: refill the ring when this round would read past it ----------------
         if (tfill < t + NT) {
-            const Philox4 w = chain_words((uint32_t)(tfill + tid), key0, key1, PHILOX_STREAM_STEP);
+            const Philox4 w = step_words<FULL>((uint32_t)(tfill + tid), key0, key1, (uint32_t)(N * N));
             ring[(tfill + tid) & (RING - 1)] = make_uint4(w.x, w.y, w.z, w.w);
             tfill += NT;
             cta_sync();

@@ -232,6 +232,15 @@ class Engine:
         _lib.check(self._lib.mcq_philox4x32_10_device(self._h, ctr.shape[0], ctr.ctypes.data, key.ctypes.data, out.ctypes.data))
         return out
 
+    def philox2_device(self, counters, keys):
+        """Philox2x32-10 as compiled for the GPU: counters [n, 2], keys [n] -> words [n, 2]; key 0x243F6A88 takes the
+        compiled-constant path of seeds below 2^32 (known-answer tests)."""
+        ctr = np.ascontiguousarray(counters, dtype=np.uint32).reshape(-1, 2)
+        key = np.ascontiguousarray(keys, dtype=np.uint32).reshape(-1)
+        out = np.empty_like(ctr)
+        _lib.check(self._lib.mcq_philox2x32_10_device(self._h, ctr.shape[0], ctr.ctypes.data, key.ctypes.data, out.ctypes.data))
+        return out
+
     # ------------------------------------------------------------------ chains
     def run(self, mcmc_type, n, n_steps, seeds, betas=None, *, schedules=None, q=None, groups=None, init_mode="random",
             init_states=None, history="full", hist_dtype=None, accept_bits=False, n_bins=0,

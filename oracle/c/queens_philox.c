@@ -9,22 +9,25 @@
  *
  *   chain_words(i, j)    Philox4x32-10(counter = (i, seed_lo, seed_hi, j), key = (0x243F6A88, 0x85A308D3)): the
  *                        chain's 64-bit seed sits in the counter, the cipher key is a constant
- *   words of step s      (x, y, z, w) = chain_words(s, 0)
- *   extra words of s     stream j >= 1: chain_words(s, j)
  *   mulhi(a, n)          floor(a * n / 2^32): uniform on [0, n) up to n / 2^32
  *
- *   board   (experiments.py:311-319)  column ij = mulhi(x, N^2) (i = ij / N, j = ij % N);
- *           new height = (old + 1 + mulhi(y, N - 1)) mod N: uniform over the N-1 OTHER heights,
- *           the distribution of the reference's redraw loop.
- *   full_3d (experiments.py:221-231)  queen q = mulhi(x, Q); the new cell is the first EMPTY one
+ *   board   (experiments.py:311-319)  a step needs 64 random bits and takes them from the two-word generator:
+ *               (x, z) = Philox2x32-10(counter = (s, seed_lo), key = 0x243F6A88 ^ seed_hi)
+ *           m = mulhi(x, N^2 (N - 1)) is one uniform index over the (column, other height) pairs, split as
+ *           column ij = mulhi(x, N^2) (i = ij / N, j = ij % N), offset d = mulhi(lo32(x * N^2), N - 1)
+ *           (m = ij (N - 1) + d exactly); new height = (old + 1 + d) mod N: uniform over the N-1 OTHER
+ *           heights, the distribution of the reference's redraw loop.
+ *   full_3d (experiments.py:221-231)  words of step s: (x, y, z, w) = chain_words(s, 0); extra words: stream
+ *           j >= 1, chain_words(s, j).  queen q = mulhi(x, Q); the new cell is the first EMPTY one
  *           (the queen's own cell counts as occupied) of the candidates
  *               mulhi(y, N^3), mulhi(w, N^3), mulhi(lo32(x * Q), N^3),
  *               then mulhi(word e & 3 of stream 1 + (e >> 2), N^3) for e = 0, 1, 2, ...
  *           with cell id c = (i * N + j) * N + k: uniform over the empty cells, the distribution
  *           of the reference's rejection loop against occ_set.
  *   accept  (experiments.py:238-239, :326-327)  delta <= 0, or U < exp(-beta_s * delta) in float64
- *           with the 53-bit uniform U = (z * 2^21 + (v >> 11)) / 2^53, v = word x of chain_words(s,
- *           0x80000000), and beta_s the float64 schedule value.  The uniform is a function
+ *           with the 53-bit uniform U = (z * 2^21 + (v >> 11)) / 2^53, z the step's uniform word above (board: the
+ *           second Philox2x32 word; full_3d: word z), v = word x of chain_words(s, 0x80000000), and beta_s
+ *           the float64 schedule value.  The uniform is a function
  *           of the step, so "drawn every step" (appendix A.1 of SURVEY.md) holds trivially.
  *
  *   initial states (mcmc_board.py:26-59, mcmc.py:20-101): words come from stream 0x40000000,
@@ -62,7 +65,25 @@ void qp_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out
     memcpy(out, c, sizeof c);
 }
 
+/* Philox2x32-10 (same paper): (L, R) -> (hi(M*L) ^ key ^ R, lo(M*L)), key += Weyl */
+void qp_philox2x32_10(const uint32_t ctr[2], uint32_t key, uint32_t out[2]) {
+    uint32_t l = ctr[0], r = ctr[1];
+    for (int round = 0; round < 10; ++round) {
+        const uint64_t p = (uint64_t)0xD256D193u * l;
+        l = (uint32_t)(p >> 32) ^ key ^ r;
+        r = (uint32_t)p;
+        key += 0x9E3779B9u;
+    }
+    out[0] = l; out[1] = r;
+}
+
 static inline uint32_t mulhi(uint32_t a, uint32_t n) { return (uint32_t)(((uint64_t)a * n) >> 32); }
+
+/* the two words of a board step */
+static void board_step_words(uint64_t seed, uint32_t step, uint32_t out[2]) {
+    const uint32_t ctr[2] = {step, (uint32_t)seed};
+    qp_philox2x32_10(ctr, 0x243F6A88u ^ (uint32_t)(seed >> 32), out);
+}
 
 /* the chain's seed sits in the counter; the cipher key is a constant (first 64 fractional bits of pi) */
 static void chain_words(uint64_t seed, uint32_t index, uint32_t stream, uint32_t out[4]) {
@@ -142,15 +163,19 @@ long qp_chain(int mode, int n, int q, int32_t *cells, long n_steps, uint64_t see
     memcpy(best_cells, cells, sizeof(int32_t) * 3 * (size_t)q);
     history[0] = (int32_t)cur;
     for (long s = 0; s < n_steps; ++s) {
-        uint32_t r[4];
-        chain_words(seed, (uint32_t)s, 0u, r);
+        uint32_t r[4], z;
         int idx, ti, tj, tk;
         if (mode == 0) {
-            idx = (int)mulhi(r[0], (uint32_t)(n * n));
+            uint32_t b[2];
+            board_step_words(seed, (uint32_t)s, b);
+            idx = (int)mulhi(b[0], (uint32_t)(n * n));
             ti = idx / n; tj = idx % n;
-            tk = cells[3 * idx + 2] + 1 + (int)mulhi(r[1], (uint32_t)(n - 1));
+            tk = cells[3 * idx + 2] + 1 + (int)mulhi(b[0] * (uint32_t)(n * n), (uint32_t)(n - 1));
             if (tk >= n) tk -= n;
+            z = b[1];
         } else {
+            chain_words(seed, (uint32_t)s, 0u, r);
+            z = r[2];
             idx = (int)mulhi(r[0], (uint32_t)q);
             uint32_t cand = mulhi(r[1], n3);
             for (int attempt = 0;; ++attempt) {
@@ -171,7 +196,7 @@ long qp_chain(int mode, int n, int q, int32_t *cells, long n_steps, uint64_t see
         const int delta = after - before;
         uint32_t lo[4];
         chain_words(seed, (uint32_t)s, 0x80000000u, lo);
-        const double u = (double)(((uint64_t)r[2] << 21) | (uint64_t)(lo[0] >> 11)) * (1.0 / 9007199254740992.0);
+        const double u = (double)(((uint64_t)z << 21) | (uint64_t)(lo[0] >> 11)) * (1.0 / 9007199254740992.0);
         const double p = exp(-betas[s] * (double)delta);
         const int acc = delta <= 0 || u < p;
         if (fabs(u - p) < 1e-6) ++near;

@@ -33,6 +33,8 @@ def load():
                                   C.c_void_p]
         lib.qp_philox4x32_10.restype = None
         lib.qp_philox4x32_10.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.qp_philox2x32_10.restype = None
+        lib.qp_philox2x32_10.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
         lib.qp_init_state.restype = C.c_int
         lib.qp_init_state.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_void_p]
         lib.qp_chain.restype = C.c_long
@@ -128,6 +130,14 @@ def philox(counter, key):
     k = (C.c_uint32 * 2)(*key)
     out = (C.c_uint32 * 4)()
     load().qp_philox4x32_10(c, k, out)
+    return tuple(out)
+
+
+def philox2(counter, key):
+    """Philox2x32-10 of the C oracle: the two words of a board step are philox2((step, seed_lo), 0x243F6A88 ^ seed_hi)."""
+    c = (C.c_uint32 * 2)(*counter)
+    out = (C.c_uint32 * 2)()
+    load().qp_philox2x32_10(c, C.c_uint32(key), out)
     return tuple(out)
 
 

@@ -23,6 +23,6 @@ eng = mcq.Engine(0)
 seeds = torch.arange(nc, dtype=torch.int64).cuda() + 42
 for _ in range(2):
     r = eng.run(mode, 12, ns, seeds, schedules={"type": "constant", "beta_const": beta}, history="stats", n_bins=100,
-                device_buffers=True, want_states=False)
+                device_buffers=True, want_states=False, init_mode=os.environ.get("MCQ_INIT", "random"))
     torch.cuda.synchronize()
 print(which, "pps %.3e" % (nc * ns / (r.kernel_ms * 1e-3)), "acc %.4f" % (float(r.n_accepted.double().mean()) / ns), "ms", r.kernel_ms)

@@ -54,6 +54,28 @@ def test_device_philox_equals_host_and_oracle(engine):
         assert tuple(out) == tuple(int(v) for v in dev[i]) == co.philox(ctr[i].tolist(), key[i].tolist())
 
 
+def test_device_philox2_equals_host_and_oracle(engine):
+    """Philox2x32-10 (board steps) as compiled for sm_100a -- both compiled forms: key 0x243F6A88 is the constant-key
+    path of seeds below 2^32 -- == the host copy == the C oracle == Random123 KATs."""
+    import ctypes as C
+    from monte_carlo_collective_b200 import _lib
+    lib = _lib.load()
+    kats = [((0, 0), 0, (0xff1dae59, 0x6cd10df2)),
+            ((0xffffffff, 0xffffffff), 0xffffffff, (0x2c3f628b, 0xab4fd7ad)),
+            ((0x243f6a88, 0x85a308d3), 0x13198a2e, (0xdd7ce038, 0xf62a4c12))]
+    rng = np.random.RandomState(11)
+    ctr = np.concatenate([np.array([k[0] for k in kats], dtype=np.uint32), rng.randint(0, 2 ** 32, size=(4093, 2), dtype=np.uint64).astype(np.uint32)])
+    key = np.concatenate([np.array([k[1] for k in kats], dtype=np.uint32), rng.randint(0, 2 ** 32, size=4093, dtype=np.uint64).astype(np.uint32)])
+    key[1000:3000] = 0x243F6A88
+    dev = engine.philox2_device(ctr, key)
+    for i, k in enumerate(kats):
+        assert tuple(int(v) for v in dev[i]) == k[2]
+    for i in list(range(0, len(ctr), 37)) + [1000, 1001, 2999]:
+        out = (C.c_uint32 * 2)()
+        lib.mcq_philox2x32_10((C.c_uint32 * 2)(*ctr[i].tolist()), int(key[i]), out)
+        assert tuple(out) == tuple(int(v) for v in dev[i]) == co.philox2(ctr[i].tolist(), int(key[i]))
+
+
 @pytest.mark.parametrize("name", sorted(SCHEDS))
 def test_device_schedules_equal_host_formulas(engine, name):
     """beta(step) evaluated on the device (experiments.py:13-77 in float64) against the host formulas: equal to the
@@ -92,7 +114,9 @@ def test_conflict_table_kernel_equals_oracle_all_schedules(engine, mode, n):
 
 
 @pytest.mark.parametrize("mode,n,algo,kw", [
+    ("board", 12, "table", {}),
     ("board", 12, "table", dict(history="stats")),           # HK = 3 instantiation: statistics in difference form
+    ("board", 12, "table", dict(lanes_per_chain=16)),        # two chains per warp, one seed below 2^32 and one above
     ("full_3d", 12, "table", dict(history="stats")),
     ("full_3d", 12, "table", dict(history="none")),          # HK = 0
     ("full_3d", 12, "table", dict(lanes_per_chain=16)),      # two chains per warp
@@ -107,6 +131,7 @@ def test_every_production_kernel_equals_oracle(engine, mode, n, algo, kw):
     ns = 20000 if n <= 12 else 6000
     sched = SCHEDS["linear"]
     seeds = np.arange(6, dtype=np.uint64) * 977 + 5
+    seeds[1::2] += np.uint64(0x9E3779B1) << np.uint64(32)    # 64-bit seeds: the key of the board generator is per chain
     kw = dict(kw)
     history = kw.pop("history", "full")
     r = engine.run(mode, n, ns, seeds, schedules=sched, history=history, accept_bits=True, algo=algo, **kw)

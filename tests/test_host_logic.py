@@ -92,7 +92,7 @@ def test_c_abi_exports_every_declared_symbol():
         getattr(lib, name)
     assert declared == {name for name, _, _ in _lib.SYMBOLS}
     lib = _lib.load()
-    assert lib.mcq_abi_version() == 3
+    assert lib.mcq_abi_version() == 4
     assert lib.mcq_sizeof_run_params() == C.sizeof(_lib.RunParams)
     # every field of the ctypes mirror appears in the header struct, in order
     body = header[header.index("typedef struct mcq_run_params {"): header.index("} mcq_run_params;")]
@@ -111,6 +111,21 @@ def test_philox_known_answers():
         out = (C.c_uint32 * 4)()
         lib.mcq_philox4x32_10((C.c_uint32 * 4)(*ctr), (C.c_uint32 * 2)(*key), out)
         assert tuple(out) == want
+
+
+def test_philox2_known_answers():
+    """Random123 kat_vectors, philox2x32 with 10 rounds (the generator of board steps)."""
+    from monte_carlo_collective_b200 import _lib
+    lib = _lib.load()
+    for ctr, key, want in PHILOX2_KATS:
+        out = (C.c_uint32 * 2)()
+        lib.mcq_philox2x32_10((C.c_uint32 * 2)(*ctr), key, out)
+        assert tuple(out) == want
+
+
+PHILOX2_KATS = [((0, 0), 0, (0xff1dae59, 0x6cd10df2)),
+                ((0xffffffff, 0xffffffff), 0xffffffff, (0x2c3f628b, 0xab4fd7ad)),
+                ((0x243f6a88, 0x85a308d3), 0x13198a2e, (0xdd7ce038, 0xf62a4c12))]
 
 
 def test_geometry_queries_and_argument_checks():

@@ -147,6 +147,33 @@ def test_oracle_philox_known_answers():
     assert co.philox((0xffffffff,) * 4, (0xffffffff,) * 2) == (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)
     assert co.philox((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0)) == \
         (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1)
+    # Philox2x32-10, the two-word generator of board steps
+    assert co.philox2((0, 0), 0) == (0xff1dae59, 0x6cd10df2)
+    assert co.philox2((0xffffffff, 0xffffffff), 0xffffffff) == (0x2c3f628b, 0xab4fd7ad)
+    assert co.philox2((0x243f6a88, 0x85a308d3), 0x13198a2e) == (0xdd7ce038, 0xf62a4c12)
+
+
+def test_board_step_words_follow_the_documented_mapping():
+    """The first recorded move of a board chain, re-derived in Python from the oracle's Philox2x32-10:
+    (x, z) = philox2((s, seed_lo), 0x243F6A88 ^ seed_hi); column = mulhi(x, N^2); offset = mulhi(lo32(x N^2), N - 1);
+    U = (z 2^21 + (v >> 11)) / 2^53 with v = word 0 of Philox4x32-10((s, seed_lo, seed_hi, 0x80000000), pi key)."""
+    from oracle import c_oracle as co
+    n = 9
+    for seed in (3, 0x1_0000_0005, 0xDEADBEEF_12345678):
+        state = co.philox_init_state("board", n, "random", seed)
+        r = co.philox_chain("board", n, seed, np.full(3, 0.7), state=state, record=True)
+        cur = state.copy()
+        for s in range(3):
+            x, z = co.philox2((s, seed & 0xffffffff), 0x243F6A88 ^ (seed >> 32))
+            col = (x * n * n) >> 32
+            d = (((x * n * n) & 0xffffffff) * (n - 1)) >> 32
+            i, j = divmod(col, n)
+            k = (int(cur[i, j]) + 1 + d) % n
+            assert tuple(int(v) for v in r["moves"][s][:3]) == (i, j, k)
+            v = co.philox((s, seed & 0xffffffff, seed >> 32, 0x80000000), (0x243F6A88, 0x85A308D3))[0]
+            assert r["uniforms"][s] == ((z << 21) | (v >> 11)) / 2.0 ** 53
+            if r["accepted"][s]:
+                cur[i, j] = k
 
 
 @pytest.mark.parametrize("mode", ["board", "full_3d"])
