@@ -706,7 +706,7 @@ int mcq_run(mcq_ctx *ctx, const mcq_run_params *p) {
     if (use_wide && replay) return fail(MCQ_EINVAL, "MCQ_ALGO_WIDE does not replay recorded streams");
     {
         const Layout l1 = make_layout(full, p->n, p->q, 1);
-        const size_t need = (size_t)l1.off_pkt + 2 * 32 * 16 + WIDE_XCH_BYTES;   // narrowest CTA
+        const size_t need = (size_t)l1.off_pkt + 2 * 32 * 16 + WIDE_XCH_BYTES + 2 * WIDE_REC_WORDS * 4;   // narrowest CTA
         if (p->algo == MCQ_ALGO_AUTO && !use_spec && !replay && G == 0 && need <= smem_block) use_wide = true;
     }
     if (use_wide) use_gmem = false;
@@ -717,20 +717,20 @@ int mcq_run(mcq_ctx *ctx, const mcq_run_params *p) {
     }
     Layout lay = make_layout(full, p->n, p->q, G);
     // CTA-per-chain kernel: 8, 4, 2 or 1 warps per chain.  What counts first is how many chains an SM holds (shared
-    // memory: counters + state + a ring of 2 * threads steps; registers: 128 per thread).  Among the widths that
+    // memory: counters + state + a ring of 2 * threads steps; registers: 144 per thread).  Among the widths that
     // reach that residency: one warp up to N = 40 (no block barrier at all), two warps beyond (measured, round 2:
     // N = 22..40 run 8-25 % faster on one warp than on two; N = 48 and 64 are 4-10 % faster on two warps than on
     // one or four).  warps_per_cta = 1, 2, 4, 8 overrides.
     const int w_best = lay.off_pkt, w_ring = lay.off_pkt;   // (the best state is kept in global memory: no shared copy)
     int wide_threads = WIDE_THREADS;
-    auto wide_bytes = [&](int nt) { return (size_t)w_ring + 2 * (size_t)nt * 16 + WIDE_XCH_BYTES; };
+    auto wide_bytes = [&](int nt) { return (size_t)w_ring + 2 * (size_t)nt * 16 + WIDE_XCH_BYTES + 2 * (size_t)(nt / 32) * WIDE_REC_WORDS * 4; };
     if (use_wide) {
         const long long want = (nc + ctx->prop.multiProcessorCount - 1) / ctx->prop.multiProcessorCount;   // chains per SM on offer
         long long best_conc = 0;
         const int preferred = p->n <= 40 ? 32 : 64;
         auto residency = [&](int nt) -> long long {
             if (wide_bytes(nt) > smem_block) return 0;
-            const long long by_smem = (long long)(smem_sm / (wide_bytes(nt) + 1024)), by_regs = 65536 / (128 * nt);
+            const long long by_smem = (long long)(smem_sm / (wide_bytes(nt) + 1024)), by_regs = 65536 / (144 * nt);
             return std::min(want, std::min<long long>(32, std::min(by_smem, by_regs)));
         };
         for (int nt = 32; nt <= 256; nt <<= 1) best_conc = std::max(best_conc, residency(nt));   // (non-increasing in nt)

@@ -54,6 +54,11 @@ __global__ void __launch_bounds__(NT, 1) wide_kernel(const __grid_constant__ KAr
     int *jcount = xch + 3 * NW;                                       // entries in the journal; > WIDE_JCAP: overflowed
     uint16_t *jrn = reinterpret_cast<uint16_t *>(xch + 3 * NW + 1);
     uint32_t *xmv = reinterpret_cast<uint32_t *>(xch) + 64;           // [NW][3]: old cell, new cell, queen of each warp's first acceptance
+    // board chains without early stop commit every accepted proposal of a round that the earlier commits of the
+    // round cannot have touched (see the commit loop): [2][NW] records of a committing thread's 24 line indices + move
+    constexpr bool MULTI = !FULL && !EARLY;
+    [[maybe_unused]] uint32_t *xrec = reinterpret_cast<uint32_t *>(smem + a.w_xch + WIDE_XCH_BYTES);
+    [[maybe_unused]] int rec_par = 0;
 
     // ---- build the slab from the external state ----
     {
@@ -148,7 +153,17 @@ __global__ void __launch_bounds__(NT, 1) wide_kernel(const __grid_constant__ KAr
             tfill += NT;
             cta_sync();
         }
-        const int rem = min(a.t_end - t, width);
+        if constexpr (MULTI) {
+            // a round of the multi-commit form never crosses the edge of an acceptance bin: bins that ended are closed
+            // here (every acceptance so far lies before t), and the round stops at the next edge
+            while (t >= next_edge) {
+                if (tid == 0 && a.acc_hist) a.acc_hist[(size_t)chain * a.n_bins + bin] = (uint32_t)(n_acc - bin_mark);
+                bin_mark = n_acc;
+                ++bin;
+                next_edge = a.bin_starts[bin + 1];
+            }
+        }
+        const int rem = MULTI ? min(min(a.t_end, next_edge) - t, width) : min(a.t_end - t, width);
         const bool valid = tid < rem;
         const int s = min(t + tid, a.t_end - 1);          // threads past the end redo the last step, masked below
         const uint4 w = ring[s & (RING - 1)];
@@ -157,6 +172,7 @@ __global__ void __launch_bounds__(NT, 1) wide_kernel(const __grid_constant__ KAr
         // ---------------- this thread's proposal: step s against the current state ----------------
         int i0 = 0, j0 = 0, k0c = 0, i1 = 0, j1 = 0, k1c = 0, qsel = 0, dE = 0;
         bool accept = false, was_near = false, was_flip = false;
+        int io[NFAM], in[NFAM];   // the counters of the old and the new cell, per family
         if (tid < width) {
         if constexpr (FULL) {
             qsel = (int)__umulhi(w.x, (uint32_t)a.Q);
@@ -189,7 +205,6 @@ __global__ void __launch_bounds__(NT, 1) wide_kernel(const __grid_constant__ KAr
         }
         // delta-E from the line counters: old_conf = sum(co - 1), new_conf = sum(cn) - [shared line]
         {
-            int io[NFAM], in[NFAM];
             auto both = [&](auto fc) {
                 constexpr int f = decltype(fc)::value;
                 if constexpr (f >= F0) {
@@ -226,6 +241,116 @@ __global__ void __launch_bounds__(NT, 1) wide_kernel(const __grid_constant__ KAr
         accept = accept && valid;
         }
 
+        if constexpr (MULTI) {
+            // ---------------- the CTA commits every accepted proposal the earlier commits cannot have touched ----------------
+            // A proposal reads 24 counters and its column's height.  A committed move changes 24 counters and one
+            // height, so a LATER thread's delta-E -- and with it its accept decision, a function of (delta-E, step)
+            // alone -- stands unless one of its 24 counters is among those 24 (a move in the same column shares the old
+            // cell's lines): at N = 64 that is about 1 % of the later threads per commit.  The commits of a round are
+            // found in step order; after each one the later threads compare their counter indices with the committed
+            // move's, and the round ends before the first thread that was touched (it is evaluated again next round).
+            // The chain is the sequential one of experiments.py:308-355, step for step; a round retires several
+            // accepted moves instead of one.
+            int limit = rem, from = 0, e_run = 0, e_mine = 0;
+            bool stale_me = false;
+            for (;;) {
+                // the earliest thread that is stale (low half 0) or accepts (delta-E, biased, in the low half)
+                int mine = NONE;
+                if (tid >= from && tid < limit) {
+                    if (stale_me) mine = tid << 16;
+                    else if (accept) mine = (tid << 16) | (dE + 0x8000);
+                }
+                const int wmin = __reduce_min_sync(FULLMASK, mine);
+                int cmin = wmin;
+                if (mine == wmin && (mine & 0xffff) != 0 && mine != NONE) {   // this warp's candidate publishes its record
+                    uint4 *rec = reinterpret_cast<uint4 *>(xrec + (rec_par * NW + warp) * WIDE_REC_WORDS);
+                    rec[0] = make_uint4((uint32_t)io[1], (uint32_t)io[2], (uint32_t)io[3], (uint32_t)io[4]);
+                    rec[1] = make_uint4((uint32_t)io[5], (uint32_t)io[6], (uint32_t)io[7], (uint32_t)io[8]);
+                    rec[2] = make_uint4((uint32_t)io[9], (uint32_t)io[10], (uint32_t)io[11], (uint32_t)io[12]);
+                    rec[3] = make_uint4((uint32_t)in[1], (uint32_t)in[2], (uint32_t)in[3], (uint32_t)in[4]);
+                    rec[4] = make_uint4((uint32_t)in[5], (uint32_t)in[6], (uint32_t)in[7], (uint32_t)in[8]);
+                    rec[5] = make_uint4((uint32_t)in[9], (uint32_t)in[10], (uint32_t)in[11], (uint32_t)in[12]);
+                    rec[6] = make_uint4((uint32_t)(i0 * N + j0), (uint32_t)k1c, 0u, 0u);
+                }
+                if constexpr (NT > 32) {
+                    if (lane == 0) xch[rec_par * NW + warp] = wmin;
+                    __syncthreads();
+                    cmin = __reduce_min_sync(FULLMASK, lane < NW ? xch[rec_par * NW + lane] : NONE);
+                } else {
+                    __syncwarp();
+                }
+                if (cmin == NONE) break;
+                const int c = cmin >> 16;
+                if ((cmin & 0xffff) == 0) { limit = c; break; }   // touched by an earlier commit: the round ends before it
+                const int dEc = (cmin & 0xffff) - 0x8000;
+                const uint4 *wr = reinterpret_cast<const uint4 *>(xrec + (rec_par * NW + (c >> 5)) * WIDE_REC_WORDS);
+                rec_par ^= 1;
+                // later threads: is one of my counters among the 24 this move changes?
+                if (tid > c && tid < limit && !stale_me) {
+                    const uint4 o0 = wr[0], o1 = wr[1], o2 = wr[2], n0 = wr[3], n1 = wr[4], n2 = wr[5];
+                    const int co[12] = {(int)o0.x, (int)o0.y, (int)o0.z, (int)o0.w, (int)o1.x, (int)o1.y, (int)o1.z, (int)o1.w,
+                                        (int)o2.x, (int)o2.y, (int)o2.z, (int)o2.w};
+                    const int cn[12] = {(int)n0.x, (int)n0.y, (int)n0.z, (int)n0.w, (int)n1.x, (int)n1.y, (int)n1.z, (int)n1.w,
+                                        (int)n2.x, (int)n2.y, (int)n2.z, (int)n2.w};
+                    bool hit = false;
+#pragma unroll
+                    for (int f = 1; f < NFAM; ++f)
+                        hit |= (io[f] == co[f - 1]) | (io[f] == cn[f - 1]) | (in[f] == co[f - 1]) | (in[f] == cn[f - 1]);
+                    stale_me = hit;
+                }
+                // the move is applied: lane f of the committing thread's warp owns family f, the thread itself the rest.
+                // (the commits of one round touch disjoint counters and columns, so their updates need no order)
+                if (warp == (c >> 5) && lane >= 1 && lane < NFAM) {
+                    const uint32_t *w32 = reinterpret_cast<const uint32_t *>(wr);
+                    const int o = (int)w32[lane - 1], n = (int)w32[12 + lane - 1];
+                    const int vo = cnt[o], vn = cnt[n];
+                    cnt[o] = (uint8_t)(vo - 1); cnt[n] = (uint8_t)(vn + 1);
+                }
+                const int E_old = E + e_run, E_new = E_old + dEc;
+                if (tid == c) {
+                    const int col = i0 * N + j0;
+                    const int jn = jfresh ? 0 : *jcount;
+                    if (jn < WIDE_JCAP) jrn[jn] = (uint16_t)col;
+                    *jcount = jn + 1;   // WIDE_JCAP + 1 and beyond: overflow, the next snapshot is a full copy
+                    st[col] = (unsigned char)k1c;
+                    if (a.dsum_e && dEc != 0) stat_delta(a, grp, (long long)t + c + 1, E_old, E_new, 0);
+                    if (abits_row) atomicOr(abits_row + ((t + c) >> 5), 1u << ((t + c) & 31));
+                }
+                jfresh = false;
+                if (tid >= c) e_mine += dEc;
+                e_run += dEc;
+                ++n_acc;
+                if (E_new < best) {
+                    // snapshot: the state at the first visit of the minimum (strict <, experiments.py:340), i.e. right
+                    // after THIS commit -- the elements moved since the previous snapshot go to the global copy
+                    best = E_new;
+                    best_step = t + c + 1;
+                    cta_sync();
+                    const int jn = *jcount;
+                    if (jn <= WIDE_JCAP) {
+                        for (int e = tid; e < jn; e += NT) best_out[jrn[e]] = st[jrn[e]];
+                    } else {
+                        for (int el = tid; el < a.Q; el += NT) best_out[el] = st[el];
+                    }
+                    jfresh = true;
+                    cta_sync();   // (the journal restarts at the next commit)
+                }
+                from = c + 1;
+            }
+            const int adv = limit;   // steps consumed: all of the round, or up to the first touched thread
+            if (was_near && tid < adv) { ++near; flips += (uint32_t)was_flip; }
+            if (tid < adv && a.hist_kind) {
+                const int v = E + e_mine;
+                if (a.hist_kind == 1) reinterpret_cast<uint16_t *>(hrow)[s + 1] = (uint16_t)v;
+                else reinterpret_cast<int *>(hrow)[s + 1] = v;
+            }
+            cta_sync();   // counters and state are final before the next round reads them
+            E += e_run;
+            t += adv;
+            if (adv * 2 > width) width = min(NT, width * 2);
+            else if (adv * 8 < width) width = max(32, width >> 1);
+            continue;
+        }
         // ---------------- the CTA commits its first accepted proposal ----------------
         // thread index in the high half, delta-E (biased) in the low half: the minimum over the CTA is the first
         // accepting thread together with its delta-E
