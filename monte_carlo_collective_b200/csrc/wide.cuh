@@ -55,10 +55,9 @@ __global__ void __launch_bounds__(NT, 1) wide_kernel(const __grid_constant__ KAr
     uint16_t *jrn = reinterpret_cast<uint16_t *>(xch + 3 * NW + 1);
     uint32_t *xmv = reinterpret_cast<uint32_t *>(xch) + 64;           // [NW][3]: old cell, new cell, queen of each warp's first acceptance
     // board chains without early stop commit every accepted proposal of a round that the earlier commits of the
-    // round cannot have touched (see the commit loop): [2][NW] records of a committing thread's 24 line indices + move
+    // round cannot have touched (see the commit block): [NT] (move, delta-E) of the accepting threads
     constexpr bool MULTI = !FULL && !EARLY;
     [[maybe_unused]] uint32_t *xrec = reinterpret_cast<uint32_t *>(smem + a.w_xch + WIDE_XCH_BYTES);
-    [[maybe_unused]] int rec_par = 0;
 
     // ---- build the slab from the external state ----
     {
@@ -243,109 +242,222 @@ __global__ void __launch_bounds__(NT, 1) wide_kernel(const __grid_constant__ KAr
 
         if constexpr (MULTI) {
             // ---------------- the CTA commits every accepted proposal the earlier commits cannot have touched ----------------
-            // A proposal reads 24 counters and its column's height.  A committed move changes 24 counters and one
-            // height, so a LATER thread's delta-E -- and with it its accept decision, a function of (delta-E, step)
-            // alone -- stands unless one of its 24 counters is among those 24 (a move in the same column shares the old
-            // cell's lines): at N = 64 that is about 1 % of the later threads per commit.  The commits of a round are
-            // found in step order; after each one the later threads compare their counter indices with the committed
-            // move's, and the round ends before the first thread that was touched (it is evaluated again next round).
-            // The chain is the sequential one of experiments.py:308-355, step for step; a round retires several
-            // accepted moves instead of one.
-            int limit = rem, from = 0, e_run = 0, e_mine = 0;
-            bool stale_me = false;
-            for (;;) {
-                // the earliest thread that is stale (low half 0) or accepts (delta-E, biased, in the low half)
-                int mine = NONE;
-                if (tid >= from && tid < limit) {
-                    if (stale_me) mine = tid << 16;
-                    else if (accept) mine = (tid << 16) | (dE + 0x8000);
-                }
-                const int wmin = __reduce_min_sync(FULLMASK, mine);
-                int cmin = wmin;
-                if (mine == wmin && (mine & 0xffff) != 0 && mine != NONE) {   // this warp's candidate publishes its record
-                    uint4 *rec = reinterpret_cast<uint4 *>(xrec + (rec_par * NW + warp) * WIDE_REC_WORDS);
-                    rec[0] = make_uint4((uint32_t)io[1], (uint32_t)io[2], (uint32_t)io[3], (uint32_t)io[4]);
-                    rec[1] = make_uint4((uint32_t)io[5], (uint32_t)io[6], (uint32_t)io[7], (uint32_t)io[8]);
-                    rec[2] = make_uint4((uint32_t)io[9], (uint32_t)io[10], (uint32_t)io[11], (uint32_t)io[12]);
-                    rec[3] = make_uint4((uint32_t)in[1], (uint32_t)in[2], (uint32_t)in[3], (uint32_t)in[4]);
-                    rec[4] = make_uint4((uint32_t)in[5], (uint32_t)in[6], (uint32_t)in[7], (uint32_t)in[8]);
-                    rec[5] = make_uint4((uint32_t)in[9], (uint32_t)in[10], (uint32_t)in[11], (uint32_t)in[12]);
-                    rec[6] = make_uint4((uint32_t)(i0 * N + j0), (uint32_t)k1c, 0u, 0u);
-                }
-                if constexpr (NT > 32) {
-                    if (lane == 0) xch[rec_par * NW + warp] = wmin;
-                    __syncthreads();
-                    cmin = __reduce_min_sync(FULLMASK, lane < NW ? xch[rec_par * NW + lane] : NONE);
-                } else {
-                    __syncwarp();
-                }
-                if (cmin == NONE) break;
-                const int c = cmin >> 16;
-                if ((cmin & 0xffff) == 0) { limit = c; break; }   // touched by an earlier commit: the round ends before it
-                const int dEc = (cmin & 0xffff) - 0x8000;
-                const uint4 *wr = reinterpret_cast<const uint4 *>(xrec + (rec_par * NW + (c >> 5)) * WIDE_REC_WORDS);
-                rec_par ^= 1;
-                // later threads: is one of my counters among the 24 this move changes?
-                if (tid > c && tid < limit && !stale_me) {
-                    const uint4 o0 = wr[0], o1 = wr[1], o2 = wr[2], n0 = wr[3], n1 = wr[4], n2 = wr[5];
-                    const int co[12] = {(int)o0.x, (int)o0.y, (int)o0.z, (int)o0.w, (int)o1.x, (int)o1.y, (int)o1.z, (int)o1.w,
-                                        (int)o2.x, (int)o2.y, (int)o2.z, (int)o2.w};
-                    const int cn[12] = {(int)n0.x, (int)n0.y, (int)n0.z, (int)n0.w, (int)n1.x, (int)n1.y, (int)n1.z, (int)n1.w,
-                                        (int)n2.x, (int)n2.y, (int)n2.z, (int)n2.w};
-                    bool hit = false;
-#pragma unroll
-                    for (int f = 1; f < NFAM; ++f)
-                        hit |= (io[f] == co[f - 1]) | (io[f] == cn[f - 1]) | (in[f] == co[f - 1]) | (in[f] == cn[f - 1]);
-                    stale_me = hit;
-                }
-                // the move is applied: lane f of the committing thread's warp owns family f, the thread itself the rest.
-                // (the commits of one round touch disjoint counters and columns, so their updates need no order)
-                if (warp == (c >> 5) && lane >= 1 && lane < NFAM) {
-                    const uint32_t *w32 = reinterpret_cast<const uint32_t *>(wr);
-                    const int o = (int)w32[lane - 1], n = (int)w32[12 + lane - 1];
-                    const int vo = cnt[o], vn = cnt[n];
-                    cnt[o] = (uint8_t)(vo - 1); cnt[n] = (uint8_t)(vn + 1);
-                }
-                const int E_old = E + e_run, E_new = E_old + dEc;
-                if (tid == c) {
-                    const int col = i0 * N + j0;
-                    const int jn = jfresh ? 0 : *jcount;
-                    if (jn < WIDE_JCAP) jrn[jn] = (uint16_t)col;
-                    *jcount = jn + 1;   // WIDE_JCAP + 1 and beyond: overflow, the next snapshot is a full copy
-                    st[col] = (unsigned char)k1c;
-                    if (a.dsum_e && dEc != 0) stat_delta(a, grp, (long long)t + c + 1, E_old, E_new, 0);
-                    if (abits_row) atomicOr(abits_row + ((t + c) >> 5), 1u << ((t + c) & 31));
-                }
-                jfresh = false;
-                if (tid >= c) e_mine += dEc;
-                e_run += dEc;
-                ++n_acc;
-                if (E_new < best) {
-                    // snapshot: the state at the first visit of the minimum (strict <, experiments.py:340), i.e. right
-                    // after THIS commit -- the elements moved since the previous snapshot go to the global copy
-                    best = E_new;
-                    best_step = t + c + 1;
-                    cta_sync();
-                    const int jn = *jcount;
-                    if (jn <= WIDE_JCAP) {
-                        for (int e = tid; e < jn; e += NT) best_out[jrn[e]] = st[jrn[e]];
-                    } else {
-                        for (int el = tid; el < a.Q; el += NT) best_out[el] = st[el];
+            // A proposal reads 24 counters and its column's height.  A committed move changes the 24 counters of the
+            // lines through its old and its new cell, and one height; so a LATER thread's delta-E -- and with it its
+            // accept decision, a function of (delta-E, step) alone -- stands unless one of its two cells lies on a line
+            // (of the 12 counted families) with one of the move's two cells, or in the move's column: about 1 % of the
+            // later threads per commit at N = 64.  All accepting threads publish their move; every thread tests its
+            // cells against the moves accepted before it; the round ends before the first thread that is touched (it is
+            // evaluated again next round) and every accepted move before that thread is committed -- they touch
+            // disjoint counters and columns, so they are applied side by side.  The chain is the sequential one of
+            // experiments.py:308-355, step for step; a round retires several accepted moves instead of one.
+            auto touches = [&](uint32_t mv) -> bool {   // does the move (i | j << 8 | old k << 16 | new k << 24) touch this thread's two cells?
+                const int di = abs(i0 - (int)(mv & 255u)), dj = abs(j0 - (int)((mv >> 8) & 255u));
+                const int c0 = (int)((mv >> 16) & 255u), c1 = (int)(mv >> 24);
+                const int mag = max(di, dj);   // a line joins the two columns only if the nonzero ones of di, dj are equal
+                const bool joined = (di == 0) | (dj == 0) | (di == dj);
+                const int d00 = abs(k0c - c0), d01 = abs(k0c - c1), d10 = abs(k1c - c0), d11 = abs(k1c - c1);
+                const bool on_line = (d00 == 0) | (d00 == mag) | (d01 == 0) | (d01 == mag) | (d10 == 0) | (d10 == mag) | (d11 == 0) | (d11 == mag);
+                return joined & (on_line | (mag == 0));   // (mag == 0: the move is in this thread's column)
+            };
+            if constexpr (NT == 32) {
+                // one warp per chain (boards up to N = 40, where lines are dense and a round rarely gets far past a
+                // commit): the commits are taken one at a time, in step order, without any shared-memory exchange
+                const uint32_t my_move = (uint32_t)(i0 | (j0 << 8) | (k0c << 16) | (k1c << 24));
+                int L = rem, from = 0, e_run = 0, e_mine = 0;
+                bool hit = false;
+                for (;;) {
+                    int mine = NONE;   // the earliest thread that is touched (low half 0) or accepts (delta-E, biased, in the low half)
+                    if (tid >= from && tid < L) {
+                        if (hit) mine = tid << 16;
+                        else if (accept) mine = (tid << 16) | (dE + 0x8000);
                     }
-                    jfresh = true;
-                    cta_sync();   // (the journal restarts at the next commit)
+                    const int cmin = __reduce_min_sync(FULLMASK, mine);
+                    if (cmin == NONE) break;
+                    const int c = cmin >> 16;
+                    if ((cmin & 0xffff) == 0) { L = c; break; }
+                    const int dEc = (cmin & 0xffff) - 0x8000;
+                    const uint32_t mv = __shfl_sync(FULLMASK, my_move, c);
+                    if (tid > c && !hit) hit = touches(mv);
+                    if (lane >= 1 && lane < NFAM) {   // lane f owns family f
+                        const int a0 = mv & 255u, b0 = (mv >> 8) & 255u, h0 = (mv >> 16) & 255u, h1 = mv >> 24;
+                        const int4 cf = a.coef[lane], cs = a.csel[lane];
+                        const int o = line_index(cf, cs, a0, b0, h0), n = line_index(cf, cs, a0, b0, h1);
+                        const int vo = cnt[o], vn = cnt[n];
+                        cnt[o] = (uint8_t)(vo - 1); cnt[n] = (uint8_t)(vn + 1);
+                    }
+                    const int E_old = E + e_run, E_new = E_old + dEc;
+                    if (tid == c) {
+                        const int col = i0 * N + j0;
+                        const int jn = jfresh ? 0 : *jcount;
+                        if (jn < WIDE_JCAP) jrn[jn] = (uint16_t)col;
+                        *jcount = jn + 1;   // WIDE_JCAP + 1 and beyond: overflow, the next snapshot is a full copy
+                        st[col] = (unsigned char)k1c;
+                        if (a.dsum_e && dEc != 0) stat_delta(a, grp, (long long)t + c + 1, E_old, E_new, 0);
+                        if (abits_row) atomicOr(abits_row + ((t + c) >> 5), 1u << ((t + c) & 31));
+                    }
+                    jfresh = false;
+                    if (tid >= c) e_mine += dEc;
+                    e_run += dEc;
+                    ++n_acc;
+                    __syncwarp();
+                    if (E_new < best) {   // snapshot: the state at the first visit of the minimum (strict <, experiments.py:340)
+                        best = E_new;
+                        best_step = t + c + 1;
+                        const int jn = *jcount;
+                        if (jn <= WIDE_JCAP) {
+                            for (int e = tid; e < jn; e += NT) best_out[jrn[e]] = st[jrn[e]];
+                        } else {
+                            for (int el = tid; el < a.Q; el += NT) best_out[el] = st[el];
+                        }
+                        jfresh = true;
+                        __syncwarp();
+                    }
+                    from = c + 1;
                 }
-                from = c + 1;
+                const int adv = L;
+                if (was_near && tid < adv) { ++near; flips += (uint32_t)was_flip; }
+                if (tid < adv && a.hist_kind) {
+                    const int v = E + e_mine;
+                    if (a.hist_kind == 1) reinterpret_cast<uint16_t *>(hrow)[s + 1] = (uint16_t)v;
+                    else reinterpret_cast<int *>(hrow)[s + 1] = v;
+                }
+                __syncwarp();   // counters and state are final before the next round reads them
+                E += e_run;
+                t += adv;
+                if (adv * 2 > width) width = min(NT, width * 2);
+                else if (adv * 8 < width) width = max(32, width >> 1);
+                continue;
             }
-            const int adv = limit;   // steps consumed: all of the round, or up to the first touched thread
+            uint2 *slot = reinterpret_cast<uint2 *>(xrec);                       // [NT] (move, delta-E) of the accepting threads
+            if (accept) slot[tid] = make_uint2((uint32_t)(i0 | (j0 << 8) | (k0c << 16) | (k1c << 24)), (uint32_t)dE);
+            const unsigned wacc = __ballot_sync(FULLMASK, accept);
+            unsigned am[NW];                                                      // accepting threads of the CTA, a word per warp
+            if constexpr (NT > 32) {
+                if (lane == 0) xch[warp] = (int)wacc;
+                __syncthreads();
+#pragma unroll
+                for (int w = 0; w < NW; ++w) am[w] = (unsigned)xch[w];
+            } else {
+                __syncwarp();
+                am[0] = wacc;
+            }
+            // moves accepted before this thread: do they touch its cells?  (and what they add to the energy)
+            bool hit = false;
+            int e_before = 0;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) {
+                if (w > warp) break;
+                unsigned m = w == warp ? (am[w] & ((1u << lane) - 1u)) : am[w];
+                while (m) {
+                    const int c = w * 32 + __ffs(m) - 1;
+                    m &= m - 1;
+                    const uint2 mv = slot[c];
+                    hit |= touches(mv.x);
+                    e_before += (int)mv.y;
+                }
+            }
+            const int jn0 = jfresh ? 0 : *jcount;   // journal entries so far (read before anyone appends: the barrier below orders it)
+            // the round ends before the first touched thread
+            int L = __reduce_min_sync(FULLMASK, (hit && tid < rem) ? tid : rem);
+            if constexpr (NT > 32) {
+                if (lane == 0) xch[NW + warp] = L;
+                __syncthreads();
+                L = __reduce_min_sync(FULLMASK, lane < NW ? xch[NW + lane] : rem);
+            }
+            const int adv = L;
+            // the committed moves in step order: energies, best energy (every thread, uniform)
+            int n_com = 0, e_run = 0, k_best = -1;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) {
+                unsigned m = am[w];
+                if (w * 32 + 32 > L) m &= (w * 32 >= L) ? 0u : ((1u << (L - w * 32)) - 1u);
+                am[w] = m;   // from here on: the committing threads
+                while (m) {
+                    const int c = w * 32 + __ffs(m) - 1;
+                    m &= m - 1;
+                    e_run += (int)slot[c].y;
+                    if (E + e_run < best) { best = E + e_run; best_step = t + c + 1; k_best = n_com; }
+                    ++n_com;
+                }
+            }
+            // counters: thread group g of 12 applies committed move g (13 threads per group, one idle: family 0 is not counted)
+            {
+                const int grp12 = tid / 12, fam = tid - grp12 * 12 + 1;
+                constexpr int GROUPS = NT / 12;
+                for (int g0 = 0; g0 < n_com; g0 += GROUPS) {
+                    const int g = g0 + grp12;
+                    if (grp12 < GROUPS && g < n_com) {
+                        // the g-th committing thread
+                        int c = -1, left = g;
+#pragma unroll
+                        for (int w = 0; w < NW; ++w) {
+                            const int pc = __popc(am[w]);
+                            if (c < 0 && left < pc) {
+                                unsigned m = am[w];
+                                for (int i = 0; i < left; ++i) m &= m - 1;   // (a handful of commits per round)
+                                c = w * 32 + __ffs(m) - 1;
+                            }
+                            left -= pc;
+                        }
+                        const uint32_t mvx = slot[c].x;
+                        const int a0 = mvx & 255u, b0 = (mvx >> 8) & 255u, h0 = (mvx >> 16) & 255u, h1 = mvx >> 24;
+                        const int4 cf = a.coef[fam], cs = a.csel[fam];
+                        const int o = line_index(cf, cs, a0, b0, h0), n = line_index(cf, cs, a0, b0, h1);
+                        const int vo = cnt[o], vn = cnt[n];
+                        cnt[o] = (uint8_t)(vo - 1); cnt[n] = (uint8_t)(vn + 1);
+                    }
+                }
+            }
+            // state, journal, statistics, accept bitmap: every committing thread for itself
+            const bool commits = accept && tid < L;
+            int my_k = 0;   // index of this thread's commit in the round
+#pragma unroll
+            for (int w = 0; w < NW; ++w)
+                if (w < warp) my_k += __popc(am[w]);
+                else if (w == warp) my_k += __popc(am[w] & ((1u << lane) - 1u));
+            if constexpr (NT == 32) __syncwarp();
+            auto commit_state = [&](int k_lo, int k_hi, int jbase) {   // commits k_lo .. k_hi-1; journal slot = jbase + k
+                if (commits && my_k >= k_lo && my_k < k_hi) {
+                    const int col = i0 * N + j0;
+                    const int jn = jbase + my_k;
+                    if (jn < WIDE_JCAP) jrn[jn] = (uint16_t)col;
+                    st[col] = (unsigned char)k1c;
+                }
+            };
+            if (commits) {
+                if (a.dsum_e && dE != 0) stat_delta(a, grp, (long long)t + tid + 1, E + e_before, E + e_before + dE, 0);
+                if (abits_row) atomicOr(abits_row + ((t + tid) >> 5), 1u << ((t + tid) & 31));
+            }
+            if (k_best >= 0) {
+                // snapshot: the state at the first visit of the minimum (strict <, experiments.py:340), i.e. right after
+                // commit k_best -- the elements moved since the previous snapshot go to the global copy
+                commit_state(0, k_best + 1, jn0);
+                cta_sync();
+                const int jn = jn0 + k_best + 1;   // (jn0 > WIDE_JCAP: the journal had overflowed)
+                if (jn <= WIDE_JCAP) {
+                    for (int e = tid; e < jn; e += NT) best_out[jrn[e]] = st[jrn[e]];
+                } else {
+                    for (int el = tid; el < a.Q; el += NT) best_out[el] = st[el];
+                }
+                cta_sync();
+                commit_state(k_best + 1, n_com, -(k_best + 1));   // the journal restarts after the snapshot
+                if (tid == 0) *jcount = n_com - (k_best + 1);
+                jfresh = false;
+            } else if (n_com) {
+                commit_state(0, n_com, jn0);
+                if (tid == 0) *jcount = jn0 + n_com;   // WIDE_JCAP + 1 and beyond: overflow, the next snapshot is a full copy
+                jfresh = false;
+            }
             if (was_near && tid < adv) { ++near; flips += (uint32_t)was_flip; }
             if (tid < adv && a.hist_kind) {
-                const int v = E + e_mine;
+                const int v = E + e_before + (accept ? dE : 0);
                 if (a.hist_kind == 1) reinterpret_cast<uint16_t *>(hrow)[s + 1] = (uint16_t)v;
                 else reinterpret_cast<int *>(hrow)[s + 1] = v;
             }
             cta_sync();   // counters and state are final before the next round reads them
             E += e_run;
+            n_acc += n_com;
             t += adv;
             if (adv * 2 > width) width = min(NT, width * 2);
             else if (adv * 8 < width) width = max(32, width >> 1);
