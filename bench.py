@@ -65,7 +65,8 @@ I_ALG_SURVEY = {"full_3d": 48.0, "board": 40.0}
 ISSUE_PER_CLK_PER_SM = 4
 # ncu measurements of the dominant kernel on the c2 workload live in profiles/r2_as_built.json (a LABELLED copy of
 # this round's capture: the run itself measures time, acceptance and clocks, not hardware counters)
-AS_BUILT_FILE = os.path.join(ROOT, "profiles", "r2_as_built.json")
+AS_BUILT_FILE = {"c2": os.path.join(ROOT, "profiles", "r2_as_built.json"),          # fast_kernel<1,5,32,12,3>
+                 "c5": os.path.join(ROOT, "profiles", "r2_as_built_wide.json")}     # wide_kernel<0,0,64> at N = 64
 
 _REAL_STDOUT = None
 
@@ -395,7 +396,9 @@ def main():
     peak = ISSUE_PER_CLK_PER_SM * eng.sm_count * f_mhz * 1e6
     peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
     hbm_peak = json.load(open(peaks_file))["hbm_gbs"] if os.path.isfile(peaks_file) else 6650.0
-    as_built = json.load(open(AS_BUILT_FILE)) if os.path.isfile(AS_BUILT_FILE) else {}
+    ab_file = AS_BUILT_FILE.get(args.workload)
+    as_built = json.load(open(ab_file)) if ab_file and os.path.isfile(ab_file) else \
+        {"source": None, "note": "no ncu capture of this workload's instantiation is attached (profiles/ holds c2's and c5's kernels)"}
     if args.workload == "c2":
         ia = i_alg(acc_rate)
         ia_binned = float(np.mean([[i_alg(p) for p in row] for row in p_bins]))

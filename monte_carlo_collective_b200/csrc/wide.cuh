@@ -20,6 +20,10 @@
 //     traffic.  The trajectory does not depend on the width -- any number of speculative steps commits the
 //     same first acceptance.
 //
+//   * board chains without early stop commit EVERY accepted proposal of a round that the earlier commits of the
+//     round cannot have touched (a geometric test on the published moves; the commit block below), not just the
+//     first: a 64-step round retires ~48 steps at the acceptance rates of an N = 64 anneal.
+//
 // Random stream, proposal rule and Metropolis test are those of anneal_kernel, bit for bit: the same seeds give
 // the same trajectory on either kernel (tests/test_gpu_production.py).
 #pragma once
