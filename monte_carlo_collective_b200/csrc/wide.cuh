@@ -1,28 +1,26 @@
 // Speculative CTA-per-chain annealing kernel on line counters (sm_100a): the large-board path.
 //
 // Boards beyond the conflict-table kernel (N > 18 full_3d, N > 21 board; C5 is N = 64 with 4096 queens)
-// keep one uint8 counter per attack line (anneal.cuh) -- 121 KB at N = 64, i.e. ONE chain per SM.  A single
-// warp stepping through such a chain is latency-bound, and one thread per chain with the counters in
-// global memory (anneal_kernel<1> + gslab) is bound by 25 random HBM sectors per proposal.  Here the whole
-// CTA works on one chain, the same way the lanes of a warp do in spec.cuh:
+// keep one uint8 counter per attack line (anneal.cuh) -- 105.6 KB at N = 64 with the folded space-diagonal
+// families, i.e. two chains per SM.  A single warp stepping through such a chain is latency-bound, and one thread
+// per chain with the counters in global memory (anneal_kernel<1> + gslab) is bound by 25 random HBM sectors per
+// proposal.  Here the whole CTA (1, 2, 4 or 8 warps) works on one chain, the same way the lanes of a warp do in
+// spec.cuh:
 //
 //   * thread l evaluates the proposal of step t+l against the current state (Philox words of step s depend on
 //     (seed, s) only and are kept in a ring of 2*blockDim steps); delta-E is 2 x 13 (12) counter loads;
-//   * the first accepted thread of the CTA is found with one ballot per warp and a minimum over the warps'
-//     candidates in shared memory; all steps before it were rejected and do not change the state, so the
-//     sequential chain of experiments.py:218-258 / :308-355 is reproduced exactly;
-//   * the move is applied by two warps side by side: lane f of the winner's warp updates the two counters of
-//     family f, a lane of the next warp the state, the occupancy and the best-state journal;
-//   * two __syncthreads per round.  At the acceptance rates of a cold chain (~1 %) a round of 256 threads
-//     retires ~90 proposals;
-//   * the number of threads that evaluate (`width`, 32..256 in whole warps) follows the acceptance rate: a hot
-//     chain commits after a handful of steps, so evaluating 256 of them would only queue up shared-memory
-//     traffic.  The trajectory does not depend on the width -- any number of speculative steps commits the
-//     same first acceptance.
-//
+//   * full_3d chains and chains with early stop commit the FIRST accepted proposal of the round: it is found with
+//     one `redux.min` per warp and a minimum over the warps' candidates in shared memory; all steps before it were
+//     rejected and do not change the state, so the sequential chain of experiments.py:218-258 / :308-355 is
+//     reproduced exactly.  The move is applied by two warps side by side: lane f of the winner's warp updates the
+//     two counters of family f, a lane of the next warp the state, the occupancy and the best-state journal;
+//     two __syncthreads per round;
 //   * board chains without early stop commit EVERY accepted proposal of a round that the earlier commits of the
-//     round cannot have touched (a geometric test on the published moves; the commit block below), not just the
-//     first: a 64-step round retires ~48 steps at the acceptance rates of an N = 64 anneal.
+//     round cannot have touched (a geometric test on the published moves; the commit block below): a 64-step round
+//     retires ~48 steps and 2.6 accepted moves at the acceptance rates of an N = 64 anneal instead of ~17 and one;
+//   * the number of threads that evaluate (`width`, 32..blockDim in whole warps) follows the steps a round
+//     consumes: a hot single-commit chain commits after a handful of steps, so evaluating 256 of them would only
+//     queue up shared-memory traffic.  The trajectory does not depend on the width.
 //
 // Random stream, proposal rule and Metropolis test are those of anneal_kernel, bit for bit: the same seeds give
 // the same trajectory on either kernel (tests/test_gpu_production.py).
