@@ -13,7 +13,6 @@ extern int g_smem_optin;   // sharedMemPerBlockOptin of the device (mcq_api.cu, 
 constexpr int BETA_PAD = 64;                  // floats behind the schedule table (fast.cuh reads past the last step of a launch)
 constexpr int WIDE_THREADS = 256;             // widest CTA (one per SM on the largest boards); 128 and 64 where more CTAs fit
 constexpr int WIDE_JCAP = 62;                 // journal of state elements changed since the last best-state snapshot
-constexpr int WIDE_REC_WORDS = 2;             // per thread: the (move, delta-E) an accepting thread publishes (multi-commit rounds)
 constexpr int WIDE_XCH_BYTES = 384;           // exchange words (3 per warp), journal count, journal, published moves (3 words per warp)
 
 cudaError_t launch_anneal(int G, const KArgs &a, bool replay, int grid, int block, size_t smem, cudaStream_t s);

@@ -706,7 +706,7 @@ int mcq_run(mcq_ctx *ctx, const mcq_run_params *p) {
     if (use_wide && replay) return fail(MCQ_EINVAL, "MCQ_ALGO_WIDE does not replay recorded streams");
     {
         const Layout l1 = make_layout(full, p->n, p->q, 1);
-        const size_t need = (size_t)l1.off_pkt + 2 * 32 * 16 + WIDE_XCH_BYTES + 32 * WIDE_REC_WORDS * 4;   // narrowest CTA
+        const size_t need = (size_t)l1.off_pkt + 2 * 32 * 16 + WIDE_XCH_BYTES + 32 * (full ? 4 : 2) * 4;   // narrowest CTA
         if (p->algo == MCQ_ALGO_AUTO && !use_spec && !replay && G == 0 && need <= smem_block) use_wide = true;
     }
     if (use_wide) use_gmem = false;
@@ -723,7 +723,7 @@ int mcq_run(mcq_ctx *ctx, const mcq_run_params *p) {
     // one or four).  warps_per_cta = 1, 2, 4, 8 overrides.
     const int w_best = lay.off_pkt, w_ring = lay.off_pkt;   // (the best state is kept in global memory: no shared copy)
     int wide_threads = WIDE_THREADS;
-    auto wide_bytes = [&](int nt) { return (size_t)w_ring + 2 * (size_t)nt * 16 + WIDE_XCH_BYTES + (size_t)nt * WIDE_REC_WORDS * 4; };
+    auto wide_bytes = [&](int nt) { return (size_t)w_ring + 2 * (size_t)nt * 16 + WIDE_XCH_BYTES + (size_t)nt * (full ? 4 : 2) * 4; };   // + a record per thread (multi-commit rounds)
     if (use_wide) {
         const long long want = (nc + ctx->prop.multiProcessorCount - 1) / ctx->prop.multiProcessorCount;   // chains per SM on offer
         long long best_conc = 0;

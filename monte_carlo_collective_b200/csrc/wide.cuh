@@ -9,13 +9,13 @@
 //
 //   * thread l evaluates the proposal of step t+l against the current state (Philox words of step s depend on
 //     (seed, s) only and are kept in a ring of 2*blockDim steps); delta-E is 2 x 13 (12) counter loads;
-//   * full_3d chains and chains with early stop commit the FIRST accepted proposal of the round: it is found with
+//   * chains with early stop commit the FIRST accepted proposal of the round: it is found with
 //     one `redux.min` per warp and a minimum over the warps' candidates in shared memory; all steps before it were
 //     rejected and do not change the state, so the sequential chain of experiments.py:218-258 / :308-355 is
 //     reproduced exactly.  The move is applied by two warps side by side: lane f of the winner's warp updates the
 //     two counters of family f, a lane of the next warp the state, the occupancy and the best-state journal;
 //     two __syncthreads per round;
-//   * board chains without early stop commit EVERY accepted proposal of a round that the earlier commits of the
+//   * chains without early stop commit EVERY accepted proposal of a round that the earlier commits of the
 //     round cannot have touched (a geometric test on the published moves; the commit block below): a 64-step round
 //     retires ~48 steps and 2.6 accepted moves at the acceptance rates of an N = 64 anneal instead of ~17 and one;
 //   * the number of threads that evaluate (`width`, 32..blockDim in whole warps) follows the steps a round
@@ -56,9 +56,10 @@ __global__ void __launch_bounds__(NT, 1) wide_kernel(const __grid_constant__ KAr
     int *jcount = xch + 3 * NW;                                       // entries in the journal; > WIDE_JCAP: overflowed
     uint16_t *jrn = reinterpret_cast<uint16_t *>(xch + 3 * NW + 1);
     uint32_t *xmv = reinterpret_cast<uint32_t *>(xch) + 64;           // [NW][3]: old cell, new cell, queen of each warp's first acceptance
-    // board chains without early stop commit every accepted proposal of a round that the earlier commits of the
-    // round cannot have touched (see the commit block): [NT] (move, delta-E) of the accepting threads
-    constexpr bool MULTI = !FULL && !EARLY;
+    // chains without early stop commit every accepted proposal of a round that the earlier commits of the round
+    // cannot have touched (see the commit block): [NT] records of the accepting threads -- (move, delta-E) in board
+    // mode, (old cell, new cell, delta-E, queen) in full_3d
+    constexpr bool MULTI = !EARLY;
     [[maybe_unused]] uint32_t *xrec = reinterpret_cast<uint32_t *>(smem + a.w_xch + WIDE_XCH_BYTES);
 
     // ---- build the slab from the external state ----
@@ -174,15 +175,17 @@ __global__ void __launch_bounds__(NT, 1) wide_kernel(const __grid_constant__ KAr
         int i0 = 0, j0 = 0, k0c = 0, i1 = 0, j1 = 0, k1c = 0, qsel = 0, dE = 0;
         bool accept = false, was_near = false, was_flip = false;
         int io[NFAM], in[NFAM];   // the counters of the old and the new cell, per family
+        [[maybe_unused]] int tries = 0, skip1 = -1;   // full_3d: occupied candidate cells skipped by this thread's draw, the first of them
         if (tid < width) {
         if constexpr (FULL) {
             qsel = (int)__umulhi(w.x, (uint32_t)a.Q);
             uint32_t word = w.y;
-            int tries = 0;
+            tries = 0;
             while (true) {
                 i1 = draw_digit(word, N); j1 = draw_digit(word, N); k1c = draw_digit(word, N);
                 const int cid1 = (i1 * N + j1) * N + k1c;
                 if (!((occ[cid1 >> 5] >> (cid1 & 31)) & 1u)) break;
+                if (tries == 0) skip1 = cid1;   // the first occupied candidate (the commit block needs it)
                 // occupied (the queen's own cell counts, experiments.py:230): redraw
                 if (tries == 0) word = w.w;
                 else if (tries == 1) word = w.x * (uint32_t)a.Q;   // what the queen draw left of word x
@@ -262,7 +265,24 @@ __global__ void __launch_bounds__(NT, 1) wide_kernel(const __grid_constant__ KAr
                 const bool on_line = (d00 == 0) | (d00 == mag) | (d01 == 0) | (d01 == mag) | (d10 == 0) | (d10 == mag) | (d11 == 0) | (d11 == mag);
                 return joined & (on_line | (mag == 0));   // (mag == 0: the move is in this thread's column)
             };
-            if constexpr (NT == 32) {
+            // full_3d: a committed move (queen from cell A to cell B) touches this thread if one of its two cells is
+            // collinear (13 families; the same cell counts) with A or B -- that also covers "my queen moved" and "my new
+            // cell got occupied" -- or if its draw skipped an occupied candidate that the move has vacated (exact for one
+            // skipped candidate; a thread that skipped several counts as touched by any move)
+            auto collinear = [](int ax, int ay, int az, int bx, int by, int bz) -> bool {
+                const int dx = abs(ax - bx), dy = abs(ay - by), dz = abs(az - bz);
+                const int m = max(dx, max(dy, dz));
+                return ((dx == 0) | (dx == m)) & ((dy == 0) | (dy == m)) & ((dz == 0) | (dz == m));
+            };
+            auto touches_full = [&](uint32_t A, uint32_t B) -> bool {
+                const int ax = A & 255u, ay = (A >> 8) & 255u, az = (A >> 16) & 255u;
+                const int bx = B & 255u, by = (B >> 8) & 255u, bz = (B >> 16) & 255u;
+                bool tch = collinear(i0, j0, k0c, ax, ay, az) | collinear(i0, j0, k0c, bx, by, bz) |
+                           collinear(i1, j1, k1c, ax, ay, az) | collinear(i1, j1, k1c, bx, by, bz);
+                tch |= (tries >= 2) | (tries == 1 && skip1 == (ax * N + ay) * N + az);
+                return tch;
+            };
+            if constexpr (NT == 32 && !FULL) {
                 // one warp per chain (boards up to N = 40, where lines are dense and a round rarely gets far past a
                 // commit): the commits are taken one at a time, in step order, without any shared-memory exchange
                 const uint32_t my_move = (uint32_t)(i0 | (j0 << 8) | (k0c << 16) | (k1c << 24));
@@ -331,8 +351,14 @@ __global__ void __launch_bounds__(NT, 1) wide_kernel(const __grid_constant__ KAr
                 else if (adv * 8 < width) width = max(32, width >> 1);
                 continue;
             }
-            uint2 *slot = reinterpret_cast<uint2 *>(xrec);                       // [NT] (move, delta-E) of the accepting threads
-            if (accept) slot[tid] = make_uint2((uint32_t)(i0 | (j0 << 8) | (k0c << 16) | (k1c << 24)), (uint32_t)dE);
+            // [NT] records of the accepting threads
+            uint2 *slot = reinterpret_cast<uint2 *>(xrec);   // board: (i | j << 8 | old k << 16 | new k << 24, delta-E)
+            uint4 *slot4 = reinterpret_cast<uint4 *>(xrec);  // full_3d: (old cell, new cell, delta-E, queen), cells as i | j << 8 | k << 16
+            if (accept) {
+                if constexpr (FULL) slot4[tid] = make_uint4((uint32_t)(i0 | (j0 << 8) | (k0c << 16)), (uint32_t)(i1 | (j1 << 8) | (k1c << 16)), (uint32_t)dE, (uint32_t)qsel);
+                else slot[tid] = make_uint2((uint32_t)(i0 | (j0 << 8) | (k0c << 16) | (k1c << 24)), (uint32_t)dE);
+            }
+            auto slot_dE = [&](int c) -> int { return FULL ? (int)slot4[c].z : (int)slot[c].y; };
             const unsigned wacc = __ballot_sync(FULLMASK, accept);
             unsigned am[NW];                                                      // accepting threads of the CTA, a word per warp
             if constexpr (NT > 32) {
@@ -354,9 +380,15 @@ __global__ void __launch_bounds__(NT, 1) wide_kernel(const __grid_constant__ KAr
                 while (m) {
                     const int c = w * 32 + __ffs(m) - 1;
                     m &= m - 1;
-                    const uint2 mv = slot[c];
-                    hit |= touches(mv.x);
-                    e_before += (int)mv.y;
+                    if constexpr (FULL) {
+                        const uint4 mv = slot4[c];
+                        hit |= touches_full(mv.x, mv.y);
+                        e_before += (int)mv.z;
+                    } else {
+                        const uint2 mv = slot[c];
+                        hit |= touches(mv.x);
+                        e_before += (int)mv.y;
+                    }
                 }
             }
             const int jn0 = jfresh ? 0 : *jcount;   // journal entries so far (read before anyone appends: the barrier below orders it)
@@ -378,15 +410,15 @@ __global__ void __launch_bounds__(NT, 1) wide_kernel(const __grid_constant__ KAr
                 while (m) {
                     const int c = w * 32 + __ffs(m) - 1;
                     m &= m - 1;
-                    e_run += (int)slot[c].y;
+                    e_run += slot_dE(c);
                     if (E + e_run < best) { best = E + e_run; best_step = t + c + 1; k_best = n_com; }
                     ++n_com;
                 }
             }
-            // counters: thread group g of 12 applies committed move g (13 threads per group, one idle: family 0 is not counted)
+            // counters: thread group g (one thread per counted family: 12 in board mode, 13 in full_3d) applies committed move g
             {
-                const int grp12 = tid / 12, fam = tid - grp12 * 12 + 1;
-                constexpr int GROUPS = NT / 12;
+                constexpr int GS = NFAM - F0, GROUPS = NT / GS;
+                const int grp12 = tid / GS, fam = tid - grp12 * GS + F0;
                 for (int g0 = 0; g0 < n_com; g0 += GROUPS) {
                     const int g = g0 + grp12;
                     if (grp12 < GROUPS && g < n_com) {
@@ -402,12 +434,21 @@ __global__ void __launch_bounds__(NT, 1) wide_kernel(const __grid_constant__ KAr
                             }
                             left -= pc;
                         }
-                        const uint32_t mvx = slot[c].x;
-                        const int a0 = mvx & 255u, b0 = (mvx >> 8) & 255u, h0 = (mvx >> 16) & 255u, h1 = mvx >> 24;
                         const int4 cf = a.coef[fam], cs = a.csel[fam];
-                        const int o = line_index(cf, cs, a0, b0, h0), n = line_index(cf, cs, a0, b0, h1);
-                        const int vo = cnt[o], vn = cnt[n];
-                        cnt[o] = (uint8_t)(vo - 1); cnt[n] = (uint8_t)(vn + 1);
+                        int o, n;
+                        if constexpr (FULL) {
+                            const uint4 mv = slot4[c];
+                            o = line_index(cf, cs, (int)(mv.x & 255u), (int)((mv.x >> 8) & 255u), (int)((mv.x >> 16) & 255u));
+                            n = line_index(cf, cs, (int)(mv.y & 255u), (int)((mv.y >> 8) & 255u), (int)((mv.y >> 16) & 255u));
+                        } else {
+                            const uint32_t mvx = slot[c].x;
+                            const int a0 = mvx & 255u, b0 = (mvx >> 8) & 255u, h0 = (mvx >> 16) & 255u, h1 = mvx >> 24;
+                            o = line_index(cf, cs, a0, b0, h0); n = line_index(cf, cs, a0, b0, h1);
+                        }
+                        if (o != n) {   // (board: always; full_3d: the old and the new cell may share a line)
+                            const int vo = cnt[o], vn = cnt[n];
+                            cnt[o] = (uint8_t)(vo - 1); cnt[n] = (uint8_t)(vn + 1);
+                        }
                     }
                 }
             }
@@ -421,10 +462,18 @@ __global__ void __launch_bounds__(NT, 1) wide_kernel(const __grid_constant__ KAr
             if constexpr (NT == 32) __syncwarp();
             auto commit_state = [&](int k_lo, int k_hi, int jbase) {   // commits k_lo .. k_hi-1; journal slot = jbase + k
                 if (commits && my_k >= k_lo && my_k < k_hi) {
-                    const int col = i0 * N + j0;
                     const int jn = jbase + my_k;
-                    if (jn < WIDE_JCAP) jrn[jn] = (uint16_t)col;
-                    st[col] = (unsigned char)k1c;
+                    if constexpr (FULL) {
+                        if (jn < WIDE_JCAP) jrn[jn] = (uint16_t)qsel;
+                        const int cid0 = (i0 * N + j0) * N + k0c, cid1 = (i1 * N + j1) * N + k1c;
+                        atomicAnd(&occ[cid0 >> 5], ~(1u << (cid0 & 31)));   // (two commits of a round may share a word)
+                        atomicOr(&occ[cid1 >> 5], 1u << (cid1 & 31));
+                        store_pos(st, pos32, qsel, pack_pos(pos32, i1, j1, k1c));
+                    } else {
+                        const int col = i0 * N + j0;
+                        if (jn < WIDE_JCAP) jrn[jn] = (uint16_t)col;
+                        st[col] = (unsigned char)k1c;
+                    }
                 }
             };
             if (commits) {
@@ -437,10 +486,19 @@ __global__ void __launch_bounds__(NT, 1) wide_kernel(const __grid_constant__ KAr
                 commit_state(0, k_best + 1, jn0);
                 cta_sync();
                 const int jn = jn0 + k_best + 1;   // (jn0 > WIDE_JCAP: the journal had overflowed)
+                auto put = [&](int el) {
+                    if constexpr (FULL) {
+                        int i, j, k;
+                        unpack_pos(pos32, load_pos(st, pos32, el), i, j, k);
+                        best_out[3 * el] = (uint8_t)i; best_out[3 * el + 1] = (uint8_t)j; best_out[3 * el + 2] = (uint8_t)k;
+                    } else {
+                        best_out[el] = st[el];
+                    }
+                };
                 if (jn <= WIDE_JCAP) {
-                    for (int e = tid; e < jn; e += NT) best_out[jrn[e]] = st[jrn[e]];
+                    for (int e = tid; e < jn; e += NT) put(jrn[e]);
                 } else {
-                    for (int el = tid; el < a.Q; el += NT) best_out[el] = st[el];
+                    for (int el = tid; el < a.Q; el += NT) put(el);
                 }
                 cta_sync();
                 commit_state(k_best + 1, n_com, -(k_best + 1));   // the journal restarts after the snapshot

@@ -164,26 +164,27 @@ def test_large_boards_equal_oracle(engine, n, algo):
         _compare(r, c, co.philox_chain("board", n, int(s), betas), "board", n, ns)
 
 
-@pytest.mark.parametrize("n,warps", [(64, 0), (48, 0), (33, 0), (33, 2), (64, 4), (26, 1)])
-def test_multi_commit_rounds_equal_oracle(engine, n, warps):
-    """Board rounds of the CTA-per-chain kernel commit every accepted proposal that the earlier commits of the round
-    did not touch (wide.cuh).  A hot-to-cold anneal makes rounds with many commits and many touched threads; history,
-    accept bitmap, best / final state and the binned acceptance must be the sequential chain's (the CPU oracle's)."""
-    ns = 24000
+@pytest.mark.parametrize("mode,n,warps", [("board", 64, 0), ("board", 48, 0), ("board", 33, 0), ("board", 33, 2), ("board", 64, 4), ("board", 26, 1),
+                                          ("full_3d", 24, 0), ("full_3d", 24, 2), ("full_3d", 32, 4), ("full_3d", 19, 1), ("full_3d", 9, 2)])
+def test_multi_commit_rounds_equal_oracle(engine, mode, n, warps):
+    """Rounds of the CTA-per-chain kernel commit every accepted proposal that the earlier commits of the round did not
+    touch (wide.cuh).  A hot-to-cold anneal makes rounds with many commits and many touched threads; history, accept
+    bitmap, best / final state and the binned acceptance must be the sequential chain's (the CPU oracle's)."""
+    ns = 24000 if mode == "board" else 12000
     sched = {"type": "linear_annealing", "beta_start": 0.4, "beta_end": 3.0}
     seeds = np.array([5, 6, 7 + (1 << 40)], dtype=np.uint64)
-    r = engine.run("board", n, ns, seeds, schedules=sched, history="full", accept_bits=True, n_bins=37, algo="wide", warps_per_cta=warps)
+    r = engine.run(mode, n, ns, seeds, schedules=sched, history="full", accept_bits=True, n_bins=37, algo="wide", warps_per_cta=warps)
     betas = schedules.beta_table(sched, ns)
     from monte_carlo_collective_b200.engine import bin_starts
     edges = np.asarray(bin_starts(ns, 37), dtype=np.int64)
     for c, s in enumerate(seeds):
-        want = co.philox_chain("board", n, int(s), betas)
-        _compare(r, c, want, "board", n, ns)
+        want = co.philox_chain(mode, n, int(s), betas)
+        _compare(r, c, want, mode, n, ns)
         acc = want["accepted"].astype(np.int64)
         binned = np.add.reduceat(acc, edges[:37])
         assert (np.asarray(r.accept_hist[c], dtype=np.int64) == binned).all()
     # the statistics path (difference form) sees every commit of a round
-    st = engine.run("board", n, ns, seeds, schedules=sched, history="stats", algo="wide", warps_per_cta=warps)
+    st = engine.run(mode, n, ns, seeds, schedules=sched, history="stats", algo="wide", warps_per_cta=warps)
     h = np.asarray(r.energy_history, dtype=np.int64)
     assert (np.asarray(st.stat_sum_e[0]) == h.sum(axis=0)).all()
     assert (np.asarray(st.stat_sum_e2[0]) == (h * h).sum(axis=0)).all()
