@@ -193,3 +193,41 @@ def test_no_kernel_spills_registers():
     spills = [(int(a), int(c)) for a, c in re.findall(r"(\d+) bytes spill stores, (\d+) bytes spill loads", txt)]
     assert len(spills) > 100                      # every instantiation is listed
     assert all(s == (0, 0) for s in spills), [s for s in spills if s != (0, 0)]
+
+
+def test_touch_predicates_of_the_multi_commit_rounds_equal_line_sharing():
+    """wide.cuh decides whether a committed move touches a later thread's proposal with integer arithmetic on cell
+    coordinates (`touches`, `collinear`).  Mirrors of the two predicates against the definition they replace -- the
+    two cells share one of the counted attack lines (oracle line ids, pinned to the reference by the golden energies),
+    or are the same cell -- exhaustively for small boards."""
+    from oracle import queens_numpy as qn
+
+    def collinear(a, b):                       # wide.cuh: all 13 families, the same cell counts
+        d = [abs(a[x] - b[x]) for x in range(3)]
+        m = max(d)
+        return all(v == 0 or v == m for v in d)
+
+    def touches_board(mine, move):             # wide.cuh: (i, j, old k, new k) of this thread / of the committed move
+        di, dj = abs(mine[0] - move[0]), abs(mine[1] - move[1])
+        mag = max(di, dj)
+        joined = di == 0 or dj == 0 or di == dj
+        on_line = any(abs(u - c) in (0, mag) for u in mine[2:] for c in move[2:])
+        return joined and (on_line or mag == 0)
+
+    for n in (4, 5, 7):
+        cells = [(i, j, k) for i in range(n) for j in range(n) for k in range(n)]
+        ids = {c: set(qn.line_ids(n, *c)) for c in cells}
+        for a in cells:
+            for b in cells:
+                share13 = a == b or bool(ids[a] & ids[b])
+                assert collinear(a, b) == share13, (n, a, b)
+        # board mode: family 0 (the column) is not counted, but a move in my column changes my old cell
+        ids12 = {c: {l for l in ids[c] if l[0] != 0} for c in cells}
+        rng = np.random.RandomState(n)
+        for _ in range(20000):
+            i, j, mi, mj = rng.randint(0, n, size=4)
+            k0, k1 = rng.choice(n, size=2, replace=False)
+            m0, m1 = rng.choice(n, size=2, replace=False)
+            mine_cells, move_cells = [(i, j, k0), (i, j, k1)], [(mi, mj, m0), (mi, mj, m1)]
+            want = (i, j) == (mi, mj) or any(x == y or bool(ids12[x] & ids12[y]) for x in mine_cells for y in move_cells)
+            assert touches_board((i, j, k0, k1), (mi, mj, m0, m1)) == want, (n, i, j, k0, k1, mi, mj, m0, m1)
