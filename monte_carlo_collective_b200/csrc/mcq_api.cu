@@ -718,16 +718,17 @@ int mcq_run(mcq_ctx *ctx, const mcq_run_params *p) {
     Layout lay = make_layout(full, p->n, p->q, G);
     // CTA-per-chain kernel: 8, 4, 2 or 1 warps per chain.  What counts first is how many chains an SM holds (shared
     // memory: counters + state + a ring of 2 * threads steps; registers: 144 per thread).  Among the widths that
-    // reach that residency: one warp up to N = 40 (no block barrier at all), two warps beyond (measured, round 2:
-    // N = 22..40 run 8-25 % faster on one warp than on two; N = 48 and 64 are 4-10 % faster on two warps than on
-    // one or four).  warps_per_cta = 1, 2, 4, 8 overrides.
+    // reach that residency: one warp up to N = 34 (no block barrier at all), two warps beyond (measured with the
+    // multi-commit rounds, board / full_3d: N = 28 13 % and N = 32 4 % / 5 % faster on one warp, N = 36 2 %, N = 40
+    // 9 % / 12 % and N = 44..64 8-30 % faster on two; four and eight warps are slower everywhere).
+    // warps_per_cta = 1, 2, 4, 8 overrides.
     const int w_best = lay.off_pkt, w_ring = lay.off_pkt;   // (the best state is kept in global memory: no shared copy)
     int wide_threads = WIDE_THREADS;
     auto wide_bytes = [&](int nt) { return (size_t)w_ring + 2 * (size_t)nt * 16 + WIDE_XCH_BYTES + (size_t)nt * (full ? 4 : 2) * 4; };   // + a record per thread (multi-commit rounds)
     if (use_wide) {
         const long long want = (nc + ctx->prop.multiProcessorCount - 1) / ctx->prop.multiProcessorCount;   // chains per SM on offer
         long long best_conc = 0;
-        const int preferred = p->n <= 40 ? 32 : 64;
+        const int preferred = p->n <= 34 ? 32 : 64;
         auto residency = [&](int nt) -> long long {
             if (wide_bytes(nt) > smem_block) return 0;
             const long long by_smem = (long long)(smem_sm / (wide_bytes(nt) + 1024)), by_regs = 65536 / (144 * nt);

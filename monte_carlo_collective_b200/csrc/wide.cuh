@@ -283,7 +283,7 @@ __global__ void __launch_bounds__(NT, 1) wide_kernel(const __grid_constant__ KAr
                 return tch;
             };
             if constexpr (NT == 32 && !FULL) {
-                // one warp per chain (boards up to N = 40, where lines are dense and a round rarely gets far past a
+                // one warp per chain (boards up to N = 34, where lines are dense and a round rarely gets far past a
                 // commit): the commits are taken one at a time, in step order, without any shared-memory exchange
                 const uint32_t my_move = (uint32_t)(i0 | (j0 << 8) | (k0c << 16) | (k1c << 24));
                 int L = rem, from = 0, e_run = 0, e_mine = 0;
